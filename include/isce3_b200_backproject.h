@@ -1,0 +1,274 @@
+/* isce3_b200_backproject.h -- C-ABI of the B200-native time-domain backprojection
+ * (TDBP) backend.  Plain pointers and sizes only; no C++ / CUDA / torch types.
+ *
+ * This is the drop-in boundary for ONE path of isce-framework/isce3:
+ *
+ *   isce3::cuda::focus::backproject(...)   cxx/isce3/cuda/focus/Backproject.h:78-88
+ *   isce3::focus::backproject(...)         cxx/isce3/focus/Backproject.h:37-47
+ *   isce3.cuda.focus.backproject(...)      python/extensions/pybind_isce3/cuda/focus/Backproject.cpp:25-117
+ *
+ * A thin C++ adapter (shown in INTEGRATION.md) flattens the isce3 value types
+ * (RadarGeometry, Orbit, LUT2d, DEMInterpolator, Kernel<float>, bracket params)
+ * into the descriptors below and calls i3b_backproject().  The library never
+ * throws across this boundary: every entry point returns an int status and
+ * i3b_last_error() returns the message of the last failure on this thread.
+ *
+ * All arrays are caller-owned, row-major, host memory (pageable is fine).  The
+ * callee owns every device allocation and frees it before returning (one-shot
+ * call) or at i3b_plan_destroy() (resident plan).
+ */
+#ifndef ISCE3_B200_BACKPROJECT_H
+#define ISCE3_B200_BACKPROJECT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define I3B_ABI_VERSION 1
+
+/* ---- status codes --------------------------------------------------------
+ * 0..11 mirror isce3::error::ErrorCode (cxx/isce3/error/ErrorCode.h:8-21): they
+ * are "soft" per-pixel geometry outcomes -- the call completed, failed pixels
+ * are (NaN,NaN) in `out` and NaN in `height` (Backproject.cpp:146-153,167-171).
+ * Negative codes stand for the exceptions the reference throws
+ * (cxx/isce3/except/Error.h:20-38, cuda/except/Error.h:33-66); the adapter
+ * rethrows them as the matching isce3::except type.                        */
+enum {
+    I3B_SUCCESS = 0,
+    I3B_ORBIT_INTERP_SIZE_ERROR = 1,
+    I3B_ORBIT_INTERP_DOMAIN_ERROR = 2,
+    I3B_ORBIT_INTERP_UNKNOWN_METHOD = 3,
+    I3B_OUT_OF_BOUNDS_DEM = 4,
+    I3B_INVALID_DEM = 5,
+    I3B_FAILED_TO_CONVERGE = 6,
+    I3B_WRONG_LOOK_SIDE = 7,
+    I3B_OUT_OF_BOUNDS_LOOKUP = 8,
+    I3B_NULL_DEREFERENCE = 9,
+    I3B_INVALID_TOLERANCE = 10,
+    I3B_INVALID_INTERVAL = 11,
+
+    I3B_EXC_INVALID_ARGUMENT = -1, /* isce3::except::InvalidArgument        */
+    I3B_EXC_RUNTIME_ERROR = -2,    /* isce3::except::RuntimeError (epochs,
+                                      unsupported kernel)                   */
+    I3B_EXC_DOMAIN_ERROR = -3,     /* isce3::except::DomainError (batch<1)  */
+    I3B_EXC_OVERFLOW_ERROR = -4,   /* isce3::except::OverflowError          */
+    I3B_EXC_OUT_OF_RANGE = -5,     /* isce3::except::OutOfRange (orbit)     */
+    I3B_EXC_CUDA_ERROR = -6,       /* isce3::cuda::except::CudaError        */
+    I3B_EXC_NO_DEVICE = -7         /* no usable sm_100 device: there is NO
+                                      CPU fallback in this library          */
+};
+
+/* isce3::core::LookSide (cxx/isce3/core/LookSide.h:13-17) */
+enum { I3B_LOOK_LEFT = 1, I3B_LOOK_RIGHT = -1 };
+
+/* isce3::core::OrbitInterpMethod (cxx/isce3/core/Orbit.h) */
+enum { I3B_ORBIT_HERMITE = 0, I3B_ORBIT_LEGENDRE = 1 };
+
+/* isce3::core::dataInterpMethod (cxx/isce3/core/Constants.h) subset usable by
+ * LUT2d / DEMInterpolator on this path.                                    */
+enum {
+    I3B_INTERP_SINC = 0, /* not supported -> I3B_EXC_INVALID_ARGUMENT */
+    I3B_INTERP_BILINEAR = 1,
+    I3B_INTERP_BICUBIC = 2,
+    I3B_INTERP_NEAREST = 3,
+    I3B_INTERP_BIQUINTIC = 4
+};
+
+/* isce3::focus::DryTroposphereModel (cxx/isce3/focus/DryTroposphereModel.h:15-21) */
+enum { I3B_TROPO_NODELAY = 0, I3B_TROPO_TSX = 1 };
+
+/* isce3::core::Kernel<float> dynamic types accepted by the reference CUDA path
+ * (cuda/focus/Backproject.cu:715-752).                                     */
+enum {
+    I3B_KERNEL_BARTLETT = 0,
+    I3B_KERNEL_LINEAR = 1,
+    I3B_KERNEL_KNAB = 2,
+    I3B_KERNEL_TABULATED = 3,
+    I3B_KERNEL_CHEBY = 4
+};
+
+/* isce3::product::RadarGridParameters (product/RadarGridParameters.h:43-163),
+ * already re-based to the orbit reference epoch as RadarGeometry's ctor does
+ * (container/RadarGeometry.icc:7-26).                                      */
+typedef struct {
+    double sensing_start;       /* s since ref epoch: t of line 0            */
+    double prf;                 /* Hz; line spacing is 1/prf                 */
+    double starting_range;      /* m                                         */
+    double range_pixel_spacing; /* m                                         */
+    double wavelength;          /* m (informational; the path uses c/fc)     */
+    int64_t length;             /* azimuth lines                             */
+    int64_t width;              /* range samples                             */
+    int32_t look_side;          /* I3B_LOOK_*                                */
+    int32_t _pad;
+} I3B_RadarGrid;
+
+/* isce3::core::Orbit (core/Orbit.h:193-199): uniformly sampled state vectors */
+typedef struct {
+    double t0;         /* s since ref epoch of state vector 0              */
+    double dt;         /* s                                                */
+    int32_t n;         /* number of state vectors                          */
+    int32_t method;    /* I3B_ORBIT_*                                      */
+    const double* pos; /* [n][3] ECEF m                                    */
+    const double* vel; /* [n][3] ECEF m/s                                  */
+} I3B_Orbit;
+
+/* isce3::core::LUT2d<double> (core/LUT2d.h:54-95, core/LUT2d.cpp:127-160).
+ * have_data == 0 reproduces the default-constructed LUT (eval == ref_value).*/
+typedef struct {
+    int32_t have_data;
+    int32_t bounds_error;
+    int32_t method; /* I3B_INTERP_* */
+    int32_t _pad;
+    int64_t length; /* rows  (y = azimuth time) */
+    int64_t width;  /* cols  (x = slant range)  */
+    double ref_value;
+    double xstart, ystart, dx, dy;
+    const double* data; /* [length][width] */
+} I3B_LUT2d;
+
+/* isce3::container::RadarGeometry (container/RadarGeometry.h:16-64) */
+typedef struct {
+    I3B_RadarGrid grid;
+    I3B_Orbit orbit;
+    I3B_LUT2d doppler;
+    /* orbit reference epoch, only compared for equality between the input
+     * and output geometry (Backproject.cpp:88-92): whole seconds since
+     * 1970-01-01T00:00:00 and the fractional second.                       */
+    int64_t ref_epoch_sec;
+    double ref_epoch_frac;
+} I3B_RadarGeometry;
+
+/* isce3::geometry::DEMInterpolator (geometry/DEMInterpolator.h:31-52,
+ * DEMInterpolator.cpp:592-659).  have_raster == 0 -> constant ref_height.  */
+typedef struct {
+    int32_t have_raster;
+    int32_t epsg;   /* 4326 supported for rasters; any WGS84-based code for
+                       constant-height DEMs                                 */
+    int32_t method; /* I3B_INTERP_* */
+    int32_t _pad;
+    int64_t length, width;
+    double ref_height;
+    double xstart, ystart, dx, dy; /* pixel-centre coordinates of data[0][0] */
+    const float* data;             /* [length][width] */
+} I3B_DEM;
+
+/* isce3::core::Kernel<float> (core/Kernels.h:18-172) */
+typedef struct {
+    int32_t kind;     /* I3B_KERNEL_* */
+    int32_t n;        /* table length (TABULATED) or #coeffs (CHEBY)        */
+    double width;     /* kernel.width() = 2*halfwidth                       */
+    double bandwidth; /* KNAB only                                          */
+    const float* data; /* table[n] (TABULATED, samples on [0,halfwidth]) or
+                          Chebyshev coefficients[n] (CHEBY); else NULL      */
+} I3B_Kernel;
+
+/* isce3::geometry::detail::Rdr2GeoBracketParams (geometry/detail/Rdr2Geo.h:88-97) */
+typedef struct {
+    double tol_height; /* default 1e-5 m   */
+    double look_min;   /* default 0        */
+    double look_max;   /* default pi/2     */
+} I3B_Rdr2GeoBracketParams;
+
+/* isce3::geometry::detail::Geo2RdrBracketParams (geometry/detail/Geo2Rdr.h:57-68) */
+typedef struct {
+    double tol_aztime; /* default 1e-7 s */
+    int32_t has_time_start, has_time_end;
+    double time_start, time_end;
+} I3B_Geo2RdrBracketParams;
+
+/* Everything isce3::cuda::focus::backproject takes, flattened.             */
+typedef struct {
+    uint32_t abi_version; /* = I3B_ABI_VERSION */
+    uint32_t flags;       /* I3B_FLAG_* */
+
+    float* out;      /* complex64 [out.length][out.width] interleaved re,im  */
+    const float* in; /* complex64 [in.length][in.width] range-compressed     */
+    float* height;   /* float32 [out.length][out.width] or NULL              */
+
+    I3B_RadarGeometry out_geometry;
+    I3B_RadarGeometry in_geometry;
+    I3B_DEM dem;
+    double fc; /* centre frequency, Hz */
+    double ds; /* desired azimuth resolution, m */
+    I3B_Kernel kernel;
+    int32_t dry_tropo_model; /* I3B_TROPO_* */
+    int32_t batch;           /* pulses per H2D slab (>= 1), reference default 1024 */
+    I3B_Rdr2GeoBracketParams rdr2geo;
+    I3B_Geo2RdrBracketParams geo2rdr;
+
+    /* multi-GPU extension: the output grid is cut into contiguous azimuth
+     * blocks, one per listed device, each fed only the pulses its block's
+     * apertures cover; no inter-GPU exchange.  n_devices == 0 -> the
+     * current device only (reference behaviour, focus.py:1589-1595).       */
+    int32_t n_devices;
+    const int32_t* devices;
+} I3B_BackprojectArgs;
+
+enum {
+    I3B_FLAG_NONE = 0,
+    /* force the generic accumulation kernel (evaluates the interpolation
+     * kernel exactly as core/Kernels.icc does) instead of the fast one     */
+    I3B_FLAG_FORCE_GENERIC = 1u << 0,
+    /* `in` / `out` / `height` are DEVICE pointers on the current device
+     * (no staging copies); single device only                              */
+    I3B_FLAG_DEVICE_POINTERS = 1u << 1
+};
+
+/* Per-call measurements, filled by i3b_last_stats() for the last successful
+ * i3b_backproject()/i3b_plan_execute() on this thread.  Durations are CUDA
+ * event times on the launching stream.                                     */
+typedef struct {
+    double pixel_pulses;      /* sum over pixels of (kstop - kstart)        */
+    double ms_total;          /* wall time of the whole call                */
+    double ms_h2d;            /* host->device staging of `in`               */
+    double ms_target_solve;   /* per-pixel rdr2geo/geo2rdr kernel           */
+    double ms_accumulate;     /* sum of accumulation-kernel launches        */
+    double ms_d2h;            /* device->host of out/height                 */
+    int32_t accumulate_launches;
+    int32_t total_launches;   /* all kernels of this library in the call    */
+    int32_t used_fast_kernel; /* 1 = fast path, 0 = generic                 */
+    int32_t taps;             /* ceil(kernel.width)                         */
+    int64_t h2d_bytes, d2h_bytes;
+    int32_t pulse_first, pulse_last; /* [first,last) pulses actually used   */
+    int32_t n_devices;
+} I3B_Stats;
+
+/* Device microbenchmarks used as roofline denominators (bench harness).    */
+typedef struct {
+    double fp32_tflops; /* FFMA throughput, 2 flop per FMA                  */
+    double fp64_tflops; /* DFMA throughput                                  */
+    double sfu_gops;    /* MUFU.SIN/COS ops per ns                          */
+    double sm_mhz;      /* SM clock implied by a clock64()/event pair       */
+    int32_t sm_count;
+    int32_t _pad;
+} I3B_Peaks;
+
+/* ---- entry points -------------------------------------------------------- */
+
+/* Blocking one-shot call; replaces isce3::cuda::focus::backproject
+ * (cuda/focus/Backproject.h:78-88).  Returns an I3B_* status.              */
+int i3b_backproject(const I3B_BackprojectArgs* args);
+
+/* Resident variant for callers that keep the range-compressed swath in HBM
+ * (bench `value`; a future RangeComp-on-GPU caller): create uploads `in` and
+ * the geometry, execute runs target solve + accumulation on device, download
+ * copies out/height back.                                                  */
+typedef struct I3B_Plan I3B_Plan;
+int i3b_plan_create(const I3B_BackprojectArgs* args, I3B_Plan** plan);
+int i3b_plan_execute(I3B_Plan* plan);
+int i3b_plan_download(I3B_Plan* plan, float* out, float* height);
+int i3b_plan_destroy(I3B_Plan* plan);
+
+int i3b_last_stats(I3B_Stats* stats);
+const char* i3b_last_error(void);
+const char* i3b_version(void);
+int i3b_device_count(void);
+int i3b_measure_peaks(int device, I3B_Peaks* peaks);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ISCE3_B200_BACKPROJECT_H */

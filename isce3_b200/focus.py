@@ -1,0 +1,232 @@
+"""``backproject`` with the reference's Python signature, routed to the B200 CUDA
+backend through the C-ABI of ``include/isce3_b200_backproject.h``.
+
+Mirrors python/extensions/pybind_isce3/cuda/focus/Backproject.cpp:25-117 (argument
+checks, defaults, bool return) and pybind_isce3/focus/Backproject.cpp:29-78 (the
+``rdr2geo_params`` / ``geo2rdr_params`` dict parsers).  The exceptions the
+reference throws map to Python ones the way pybind11 translates them:
+InvalidArgument -> ValueError, DomainError -> ValueError, RuntimeError ->
+RuntimeError, OverflowError -> OverflowError, OutOfRange -> IndexError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _capi
+from ._capi import Flattened
+
+
+class InvalidArgument(ValueError):
+    """isce3::except::InvalidArgument (std::invalid_argument)"""
+
+
+class DomainError(ValueError):
+    """isce3::except::DomainError (std::domain_error)"""
+
+
+class CudaError(RuntimeError):
+    """isce3::cuda::except::CudaError"""
+
+
+def parse_dry_tropo_model(s: str) -> int:
+    """isce3::focus::parseDryTropoModel (cxx/isce3/focus/DryTroposphereModel.cpp:10-21)"""
+    if s == "nodelay":
+        return _capi.TROPO_NODELAY
+    if s == "tsx":
+        return _capi.TROPO_TSX
+    raise InvalidArgument(f"unexpected dry troposphere model '{s}'")
+
+
+def parse_rdr2geo_params(params: dict) -> _capi.Rdr2GeoBracketParams:
+    out = _capi.Rdr2GeoBracketParams(1e-5, 0.0, math.pi / 2)  # geometry/detail/Rdr2Geo.h:85-97
+    for key, val in dict(params or {}).items():
+        if key in ("tol_height", "look_min", "look_max"):
+            setattr(out, key, float(val))
+        else:
+            raise InvalidArgument(f"unexpected rdr2geo_bracket keyword: {key}")
+    return out
+
+
+def parse_geo2rdr_params(params: dict) -> _capi.Geo2RdrBracketParams:
+    out = _capi.Geo2RdrBracketParams(1e-7, 0, 0, 0.0, 0.0)  # geometry/detail/Geo2Rdr.h:54-68
+    for key, val in dict(params or {}).items():
+        if key == "tol_aztime":
+            out.tol_aztime = float(val)
+        elif key == "time_start":
+            if val is not None:
+                out.has_time_start, out.time_start = 1, float(val)
+        elif key == "time_end":
+            if val is not None:
+                out.has_time_end, out.time_end = 1, float(val)
+        else:
+            raise InvalidArgument(f"unexpected geo2rdr_bracket keyword: {key}")
+    return out
+
+
+def _check_array(a, name, dtype, shape, what):
+    if not isinstance(a, np.ndarray) or a.dtype != dtype:
+        raise TypeError(f"{name} must be a numpy array of {np.dtype(dtype).name}")
+    if a.ndim != 2:
+        raise InvalidArgument(f"{what} must be 2-D")
+    if tuple(a.shape) != tuple(shape):
+        raise InvalidArgument(f"{what} shape must match {name} radar grid shape")
+    if not a.flags.c_contiguous:
+        raise TypeError(f"{name} must be C-contiguous")
+
+
+def build_args(out, out_geometry, in_, in_geometry, dem, fc, ds, kernel,
+               dry_tropo_model="tsx", rdr2geo_params=None, geo2rdr_params=None, batch=1024,
+               height=None, devices=None, force_generic=False) -> Flattened:
+    """Validate like the reference binding and flatten into an I3B_BackprojectArgs."""
+    oshape = (out_geometry.grid_length, out_geometry.grid_width)
+    ishape = (in_geometry.grid_length, in_geometry.grid_width)
+    if out is not None:
+        _check_array(out, "output", np.complex64, oshape, "output array")
+        if not out.flags.writeable:
+            raise TypeError("output array must be writeable")
+    _check_array(in_, "input", np.complex64, ishape, "input signal data")
+    if height is not None:
+        if not isinstance(height, np.ndarray) or height.dtype != np.float32:
+            raise TypeError("height must be a numpy array of float32")
+        if tuple(height.shape) != oshape:
+            raise InvalidArgument("height array shape must match output radar grid shape")
+        if not height.flags.c_contiguous:
+            raise TypeError("height must be C-contiguous")
+    atm = parse_dry_tropo_model(dry_tropo_model)
+    r2g = parse_rdr2geo_params(rdr2geo_params)
+    g2r = parse_geo2rdr_params(geo2rdr_params)
+    if int(batch) < 1:
+        raise DomainError("batch size must be > 0")
+
+    fl = Flattened()
+    a = fl.args
+    a.abi_version = _capi.ABI_VERSION
+    a.flags = _capi.FLAG_FORCE_GENERIC if force_generic else 0
+    a.out = out.ctypes.data if out is not None else None
+    a.in_ = in_.ctypes.data
+    a.height = height.ctypes.data if height is not None else None
+    fl.keep += [out, in_, height]
+    a.out_geometry = _capi.flatten_geometry(out_geometry, fl)
+    a.in_geometry = _capi.flatten_geometry(in_geometry, fl)
+    a.dem = _capi.flatten_dem(dem, fl)
+    a.fc, a.ds = float(fc), float(ds)
+    a.kernel = _capi.flatten_kernel(kernel, fl)
+    a.dry_tropo_model = atm
+    a.batch = int(batch)
+    a.rdr2geo, a.geo2rdr = r2g, g2r
+    if devices:
+        dev = np.ascontiguousarray(devices, dtype=np.int32)
+        fl.keep.append(dev)
+        a.n_devices = dev.size
+        a.devices = dev.ctypes.data_as(C.POINTER(C.c_int32))
+    return fl
+
+
+def raise_for_status(status: int, message: str):
+    """Translate an I3B_EXC_* status the way the adapter rethrows isce3 exceptions."""
+    if status >= 0:
+        return
+    table = {
+        _capi.EXC_INVALID_ARGUMENT: InvalidArgument,
+        _capi.EXC_RUNTIME_ERROR: RuntimeError,
+        _capi.EXC_DOMAIN_ERROR: DomainError,
+        _capi.EXC_OVERFLOW_ERROR: OverflowError,
+        _capi.EXC_OUT_OF_RANGE: IndexError,
+        _capi.EXC_CUDA_ERROR: CudaError,
+        _capi.EXC_NO_DEVICE: CudaError,
+    }
+    raise table.get(status, RuntimeError)(message or f"isce3_b200 error {status}")
+
+
+def last_stats() -> dict:
+    st = _capi.Stats()
+    _capi.load_library().i3b_last_stats(C.byref(st))
+    return st.as_dict()
+
+
+def backproject(out, out_geometry, in_, in_geometry, dem, fc, ds, kernel,
+                dry_tropo_model="tsx", rdr2geo_params=None, geo2rdr_params=None, batch=1024,
+                height=None, *, devices=None, force_generic=False) -> bool:
+    """Focus in azimuth via time-domain backprojection on B200.
+
+    Same positional arguments, defaults and return value as
+    ``isce3.cuda.focus.backproject`` (returns True when any pixel's geometry failed
+    to converge; those pixels are NaN).  ``devices`` (keyword-only extension) lists
+    CUDA device ordinals to shard the output grid over by azimuth block.
+    """
+    fl = build_args(out, out_geometry, in_, in_geometry, dem, fc, ds, kernel, dry_tropo_model,
+                    rdr2geo_params, geo2rdr_params, batch, height, devices, force_generic)
+    if out is None:
+        raise TypeError("output array is required")
+    lib = _capi.load_library()
+    status = lib.i3b_backproject(C.byref(fl.args))
+    if status < 0:
+        raise_for_status(status, (lib.i3b_last_error() or b"").decode())
+    return status != _capi.SUCCESS
+
+
+class BackprojectPlan:
+    """Resident variant (i3b_plan_*): the range-compressed swath and geometry are
+    uploaded once; ``execute`` runs target solve + accumulation on the device and
+    ``download`` copies the image back.  Used by bench.py for the HBM-resident
+    throughput figure."""
+
+    def __init__(self, out_geometry, in_, in_geometry, dem, fc, ds, kernel,
+                 dry_tropo_model="tsx", rdr2geo_params=None, geo2rdr_params=None, batch=1024,
+                 force_generic=False):
+        self._lib = _capi.load_library()
+        self._shape = (out_geometry.grid_length, out_geometry.grid_width)
+        fl = build_args(None, out_geometry, in_, in_geometry, dem, fc, ds, kernel,
+                        dry_tropo_model, rdr2geo_params, geo2rdr_params, batch, None, None,
+                        force_generic)
+        self._handle = C.c_void_p()
+        status = self._lib.i3b_plan_create(C.byref(fl.args), C.byref(self._handle))
+        if status < 0:
+            raise_for_status(status, (self._lib.i3b_last_error() or b"").decode())
+
+    def execute(self) -> bool:
+        status = self._lib.i3b_plan_execute(self._handle)
+        if status < 0:
+            raise_for_status(status, (self._lib.i3b_last_error() or b"").decode())
+        return status != _capi.SUCCESS
+
+    def download(self, out=None, height=None):
+        if out is None:
+            out = np.empty(self._shape, np.complex64)
+        status = self._lib.i3b_plan_download(
+            self._handle, out.ctypes.data, height.ctypes.data if height is not None else None)
+        if status < 0:
+            raise_for_status(status, (self._lib.i3b_last_error() or b"").decode())
+        return out
+
+    def stats(self) -> dict:
+        return last_stats()
+
+    def close(self):
+        if self._handle:
+            self._lib.i3b_plan_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def measure_peaks(device=0) -> dict:
+    pk = _capi.Peaks()
+    lib = _capi.load_library()
+    status = lib.i3b_measure_peaks(int(device), C.byref(pk))
+    if status < 0:
+        raise_for_status(status, (lib.i3b_last_error() or b"").decode())
+    return pk.as_dict()

@@ -1,0 +1,205 @@
+// TEST INFRASTRUCTURE -- CPU oracle for the TDBP parity tests.  Not product
+// code: only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+// --impl reference legs may build or call anything under oracle/.
+//
+// Restated 2-D samplers used by both oracle builds (the "port" in
+// tdbp_oracle.cpp and the shim classes the reference sources are compiled
+// against in oracle/_ref).  The reference implementations need
+// Eigen/GDAL/pyre and cannot be compiled here, so these follow them
+// statement by statement:
+//
+//   bilinear   cxx/isce3/core/BilinearInterpolator.cpp:13-48
+//   bicubic    cxx/isce3/core/BicubicInterpolator.cpp:35-62
+//   biquintic  cxx/isce3/core/Spline2dInterpolator.cpp:32-116 (order 6)
+//   nearest    cxx/isce3/core/NearestNeighborInterpolator.cpp:13-23
+//   LUT2d      cxx/isce3/core/LUT2d.cpp:127-160, LUT2d.h:84-95
+//   DEM        cxx/isce3/geometry/DEMInterpolator.cpp:592-659,
+//              cxx/isce3/core/Projections.h:127-133 (LonLat::forward)
+//
+// Arithmetic type U matches the reference instantiation: float for the DEM
+// raster (Matrix<float>), double for LUT2d<double>.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+
+#include "../include/isce3_b200_backproject.h"
+
+namespace tdbp_oracle {
+
+template<typename U>
+struct Grid2d {
+    const U* data;
+    long rows, cols;
+    U operator()(long r, long c) const { return data[r * cols + c]; }
+};
+
+// BilinearInterpolator.cpp:13-48
+template<typename U>
+inline U bilinear(double x, double y, const Grid2d<U>& z)
+{
+    const int x1 = (int) std::floor(x), x2 = (int) std::ceil(x);
+    const int y1 = (int) std::floor(y), y2 = (int) std::ceil(y);
+    const U q11 = z(y1, x1), q12 = z(y2, x1), q21 = z(y1, x2), q22 = z(y2, x2);
+    if (y1 == y2 && x1 == x2) return q11;
+    if (y1 == y2)
+        return U((x2 - x) / (x2 - x1)) * q11 + U((x - x1) / (x2 - x1)) * q21;
+    if (x1 == x2)
+        return U((y2 - y) / (y2 - y1)) * q11 + U((y - y1) / (y2 - y1)) * q12;
+    const U den = U((x2 - x1) * (y2 - y1));
+    return (q11 * U((x2 - x) * (y2 - y))) / den +
+           (q21 * U((x - x1) * (y2 - y))) / den +
+           (q12 * U((x2 - x) * (y - y1))) / den +
+           (q22 * U((x - x1) * (y - y1))) / den;
+}
+
+// BicubicInterpolator.cpp:29-33 (uniform Catmull-Rom between p1 and p2)
+template<typename U>
+inline U catmull_rom(U p0, U p1, U p2, U p3, double tf)
+{
+    const double tc = 1. - tf;
+    return (U(tf) * (p2 - p0 * U(tc * tc) +
+                     (p2 * U(tc * 3. + 1.) - p3 * U(tc)) * U(tf)) +
+            p1 * U(tf * tf * (tf * 3. - 5.) + 2.)) / U(2.);
+}
+
+// BicubicInterpolator.cpp:38-57
+template<typename U>
+inline U bicubic(double x, double y, const Grid2d<U>& z)
+{
+    const int x0 = (int) std::floor(x), y0 = (int) std::floor(y);
+    U rowv[4];
+    for (int i = -1; i < 3; ++i)
+        rowv[i + 1] = catmull_rom<U>(z(y0 + i, x0 - 1), z(y0 + i, x0),
+                                     z(y0 + i, x0 + 1), z(y0 + i, x0 + 2), x - x0);
+    return catmull_rom<U>(rowv[0], rowv[1], rowv[2], rowv[3], y - y0);
+}
+
+// Spline2dInterpolator.cpp:95-116 (_initSpline) and :74-93 (_spline)
+template<typename U, int N>
+inline void spline_init(const U* Y, U* R, U* Q)
+{
+    Q[0] = U(0);
+    R[0] = U(0);
+    for (int i = 1; i < N - 1; ++i) {
+        const U p = U(1.0) / (U(0.5) * Q[i - 1] + U(2.0));
+        Q[i] = U(-0.5) * p;
+        R[i] = (U(3.0) * (Y[i + 1] - U(2.0) * Y[i] + Y[i - 1]) - U(0.5) * R[i - 1]) * p;
+    }
+    R[N - 1] = U(0);
+    for (int i = N - 2; i > 0; --i) R[i] = Q[i] * R[i + 1] + R[i];
+}
+
+template<typename U, int N>
+inline U spline_eval(double x, const U* Y, const U* R)
+{
+    const U denom = U(6.0);
+    if (x < 1.0) return Y[0] + U(x - 1.0) * (Y[1] - Y[0] - (R[1] / denom));
+    if (x > N) return Y[N - 1] + U(x - N) * (Y[N - 1] - Y[N - 2] + (R[N - 2] / denom));
+    const int j = (int) std::floor(x);
+    const U xx = U(x - j);
+    const U t0 = Y[j] - Y[j - 1] - (R[j - 1] / U(3.0)) - (R[j] / denom);
+    const U t1 = xx * ((R[j - 1] / U(2.0)) + (xx * ((R[j] - R[j - 1]) / denom)));
+    return Y[j - 1] + (xx * (t0 + t1));
+}
+
+// Spline2dInterpolator.cpp:32-72 with _order = 6 (createInterpolator default,
+// core/Interpolator.h:205-214; LUT2d.cpp:181)
+template<typename U>
+inline U biquintic(double x, double y, const Grid2d<U>& z)
+{
+    constexpr int N = 6;
+    const int nx = (int) z.cols, ny = (int) z.rows;
+    int i0 = (int) y, j0 = (int) x; // even order: plain truncation
+    i0 = i0 - (N / 2) + 1;
+    j0 = j0 - (N / 2) + 1;
+    U A[N], R[N], Q[N], HC[N];
+    for (int i = 0; i < N; ++i) {
+        const int indi = std::min(std::max(i0 + i, 0), ny - 2);
+        for (int j = 0; j < N; ++j) {
+            const int indj = std::min(std::max(j0 + j, 0), nx - 2);
+            A[j] = z(indi + 1, indj + 1);
+        }
+        spline_init<U, N>(A, R, Q);
+        HC[i] = spline_eval<U, N>(x - j0, A, R);
+    }
+    spline_init<U, N>(HC, R, Q);
+    return spline_eval<U, N>(y - i0, HC, R);
+}
+
+// NearestNeighborInterpolator.cpp:13-23
+template<typename U>
+inline U nearest(double x, double y, const Grid2d<U>& z)
+{
+    return z((long) std::round(y), (long) std::round(x));
+}
+
+template<typename U>
+inline U interp2d(int method, double x, double y, const Grid2d<U>& z)
+{
+    switch (method) {
+    case I3B_INTERP_BICUBIC: return bicubic<U>(x, y, z);
+    case I3B_INTERP_BIQUINTIC: return biquintic<U>(x, y, z);
+    case I3B_INTERP_NEAREST: return nearest<U>(x, y, z);
+    default: return bilinear<U>(x, y, z); // createInterpolator fallback
+    }
+}
+
+// LUT2d.h:84-95
+inline bool lut2d_contains(const I3B_LUT2d& l, double y, double x)
+{
+    if (!l.have_data) return true;
+    const double i = (x - l.xstart) / l.dx;
+    const double j = (y - l.ystart) / l.dy;
+    return (i >= 0.0 && i <= l.width - 1.0) && (j >= 0.0 && j <= l.length - 1.0);
+}
+
+// LUT2d.cpp:127-160.  The reference logs through a pyre error channel when
+// bounds_error is set and the point is outside, then clamps and evaluates;
+// *out_of_bounds reports that condition to the caller instead.
+inline double lut2d_eval(const I3B_LUT2d& l, double y, double x, bool* out_of_bounds = nullptr)
+{
+    if (!l.have_data) return l.ref_value;
+    double xi = (x - l.xstart) / l.dx;
+    double yi = (y - l.ystart) / l.dy;
+    if (l.bounds_error && !lut2d_contains(l, y, x) && out_of_bounds) *out_of_bounds = true;
+    xi = std::min(std::max(xi, 0.0), l.width - 1.0);
+    yi = std::min(std::max(yi, 0.0), l.length - 1.0);
+    const Grid2d<double> g {l.data, (long) l.length, (long) l.width};
+    return interp2d<double>(l.method, xi, yi, g);
+}
+
+// DEMInterpolator.cpp:617-659
+inline double dem_interp_xy(const I3B_DEM& d, double x, double y)
+{
+    if (!d.have_raster) return d.ref_height;
+    if (d.epsg == 4326 && (x > 360 || x < -360)) x = std::fmod(x, 360);
+    if (d.epsg == 4326 && x < -180) x += 360;
+    if (d.epsg == 4326 && x - 360 >= d.xstart) {
+        x -= 360;
+    } else if (d.epsg == 4326 && x < d.xstart && x + 360 >= d.xstart) {
+        x += 360;
+    } else if (x < d.xstart) {
+        return d.ref_height;
+    }
+    const double row = (y - d.ystart) / d.dy;
+    const double col = (x - d.xstart) / d.dx;
+    const int irow = (int) std::floor(row);
+    const int icol = (int) std::floor(col);
+    if (irow < 2 || irow >= (int) (d.length - 1)) return d.ref_height;
+    if (icol < 2 || icol >= (int) (d.width - 1)) return d.ref_height;
+    const Grid2d<float> g {d.data, (long) d.length, (long) d.width};
+    return interp2d<float>(d.method, col, row, g);
+}
+
+// DEMInterpolator.cpp:592-611 with LonLat::forward (Projections.h:127-133).
+// Only EPSG:4326 rasters are supported by the oracle.
+inline double dem_interp_lonlat(const I3B_DEM& d, double lon, double lat)
+{
+    if (!d.have_raster) return d.ref_height;
+    const double x = lon * 180.0 / M_PI;
+    const double y = lat * 180.0 / M_PI;
+    return dem_interp_xy(d, x, y);
+}
+
+} // namespace tdbp_oracle
