@@ -1,0 +1,684 @@
+// Fast accumulation kernel of the B200 TDBP backend (sm_100a): the O(pixels x pulses)
+// hot loop, sumCoherent of cxx/isce3/focus/Backproject.cpp:30-63, re-designed for B200.
+//
+//  * CTA = 8 warps.  A CTA owns a tile of TILE_AZ x TILE_RG output pixels; every thread
+//    owns PX = 2 range-adjacent pixels; warp 0 doubles as the TMA producer.
+//  * The producer streams pulse tiles (TK range-compressed lines clipped to the
+//    range window the CTA's pixels can touch, plus the TK per-pulse orbit records) into
+//    a multi-stage shared-memory ring with TMA (cp.async.bulk.tensor.2d + cp.async.bulk)
+//    completing on mbarriers; out-of-swath samples arrive as zeros (TMA OOB fill), which
+//    IS the CPU reference's zero-padded edge window (core/detail/Interp1d.h:54-80).
+//  * Slant range stays FP64 (|x-p|^2 by FMA, sqrt by one Newton step from a linear
+//    predictor), phase and sample index are split into integer/fraction with
+//    magic-number adds, so no FP64<->FP32/int conversion instruction is issued in the loop.
+//  * Interpolation weights: per-tap polynomials in the fractional sample offset, fitted on
+//    the host to the caller's kernel (table-lerp, Chebyshev or Knab) and read from the
+//    constant bank as FFMA operands -- no shared-memory weight gathers.  Taps m and
+//    K-1-m share even/odd parts (the kernels are even functions).
+//  * The two pixels of a thread share one register window of K+1 samples read with
+//    LDS.128 (stride-16B across lanes: conflict-free).
+//
+// Numerics vs the reference: weights differ from table-lerp by the fit residual (checked
+// on the host, <= 3e-5 abs), phase fraction is quantised to 2^-23 cycle, partial sums are
+// FP32 within a pulse tile and FP64 across tiles.
+#include <cuda.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "geometry.cuh"
+#include "kernels.cuh"
+#include "launch.h"
+
+#include <climits>
+
+namespace i3b {
+
+constexpr int TILE_RG = 128;  // output range pixels per CTA tile
+constexpr int TILE_AZ = 4;    // output azimuth lines per CTA tile
+constexpr int PX = 2;         // pixels per thread (range-adjacent)
+constexpr int NTHREADS = TILE_AZ * TILE_RG / PX; // 256 threads; warp 0 is also the producer
+constexpr int TK = 16;        // pulses per stage
+constexpr int NSTAGE = 3;
+constexpr int HEADER_BYTES = 256;
+constexpr int MAX_TAPS = 32;
+constexpr int MAX_COEF = 8;   // degree <= 7
+
+// Polynomial coefficients of the per-tap weights, in f = frac - 0.5 in [-0.5, 0.5):
+//   w_m(f) = E_m(f^2) + f * O_m(f^2),  w_{K-1-m}(f) = E_m(f^2) - f * O_m(f^2)
+// c_even[m][i] multiplies f^(2i), c_odd[m][i] multiplies f^(2i+1); m < ceil(K/2).
+__constant__ float c_even[MAX_TAPS / 2 + 1][MAX_COEF / 2];
+__constant__ float c_odd[MAX_TAPS / 2 + 1][MAX_COEF / 2];
+
+// ---- PTX wrappers --------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p)
+{
+    return (uint32_t) __cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1,
+                                            uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
+                 "[%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)),
+                 "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes,
+                                             uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes "
+                 "[%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+struct FastParams {
+    long long npix;
+    int out_lines, out_width;
+    int nr, rc_k0, rc_rows;
+    int k_begin, k_end;
+    int n_pulses;   // pulses in the input grid (size of the pulse table)
+    int W;          // staged samples per pulse (even, <= 256)
+    int tiles_rg, tiles_az;
+    double G;       // samples per cycle: 1 / (fc * dtau)
+    double U0;      // swst / dtau
+    double fc;
+};
+
+constexpr double MAGIC = 805306368.0; // 1.5 * 2^29: ulp 2^-23, integer part in mantissa bits 23..
+
+// Shared-memory carve-up (dynamic): per stage [TK][W] float2 then [TK] PulseRec.
+struct SmemHeader {
+    uint64_t full[NSTAGE];
+    uint64_t empty[NSTAGE];
+    int winlo[NSTAGE];
+    int kb, ke;     // CTA pulse range
+    int bad;        // tile holds a failed pixel -> generic kernel
+    int pad;
+    double corner[4][4]; // x, y, z, fc*tau_atm of the 4 corner pixels
+};
+
+static_assert(sizeof(SmemHeader) <= HEADER_BYTES, "shared-memory header overflows its slot");
+
+__host__ __device__ inline size_t stage_bytes(int W)
+{
+    size_t b = (size_t) TK * W * sizeof(float2) + (size_t) TK * sizeof(PulseRec);
+    return (b + 127) & ~(size_t) 127;
+}
+
+// exact two-way sample coordinate u for one pixel/pulse (producer's window bounds)
+__device__ inline double sample_coord(const double* c, const PulseRec& r, double G, double U0)
+{
+    const double xx = c[0] * c[0] + c[1] * c[1] + c[2] * c[2];
+    const double r2 = fma(c[0], r.m2px, fma(c[1], r.m2py, fma(c[2], r.m2pz, xx + r.pp)));
+    const double s = sqrt(r2);
+    const double tcyc = fma(r.Cs, s, fma(c[0], r.vBx, fma(c[1], r.vBy, fma(c[2], r.vBz, c[3] + r.E))));
+    return fma(tcyc, G, -U0);
+}
+
+template<int K, int D>
+struct Weights {
+    // evaluates the K tap weights for fractional offset f (in [-0.5, 0.5))
+    __device__ static __forceinline__ void eval(float f, float (&w)[K])
+    {
+        constexpr int NE = D / 2 + 1;       // even coefficients  f^0, f^2, ...
+        constexpr int NO = (D + 1) / 2;     // odd coefficients   f^1, f^3, ...
+        const float h = f * f;
+#pragma unroll
+        for (int m = 0; m < K / 2; ++m) {
+            float e = c_even[m][NE - 1];
+#pragma unroll
+            for (int i = NE - 2; i >= 0; --i) e = fmaf(e, h, c_even[m][i]);
+            float o = c_odd[m][NO - 1];
+#pragma unroll
+            for (int i = NO - 2; i >= 0; --i) o = fmaf(o, h, c_odd[m][i]);
+            w[m] = fmaf(f, o, e);
+            w[K - 1 - m] = fmaf(-f, o, e);
+        }
+        if (K & 1) {
+            constexpr int m = K / 2;
+            float e = c_even[m][NE - 1];
+#pragma unroll
+            for (int i = NE - 2; i >= 0; --i) e = fmaf(e, h, c_even[m][i]);
+            w[m] = e;
+        }
+    }
+};
+
+// Per-pixel loop state.
+struct PixState {
+    double x, y, z, xx;   // target position, |x|^2
+    double s1, s2, yh;    // range at the two previous pulses; 0.5 / range
+    double upix;          // fc*tau_atm*G - U0 + shift
+    double mphase;        // MAGIC + fc*tau_atm
+    float accr, acci;     // FP32 partial sums of the current pulse tile
+    int kstart, kstop;
+};
+
+template<int K, int D>
+__global__ void __launch_bounds__(NTHREADS, 2)
+accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, FastParams P,
+                       const PixelRec* __restrict__ pix, const PulseRec* __restrict__ pulse,
+                       double2* __restrict__ acc, unsigned char* __restrict__ tile_generic,
+                       DevStatus* status)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    SmemHeader* hdr = reinterpret_cast<SmemHeader*>(smem_raw);
+    unsigned char* stage0 = smem_raw + HEADER_BYTES;
+    const size_t sbytes = stage_bytes(P.W);
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int tile_i = blockIdx.x % P.tiles_rg, tile_j = blockIdx.x / P.tiles_rg;
+    const int col0 = tile_i * TILE_RG, line0 = tile_j * TILE_AZ;
+
+    constexpr int LOWOFF = (K & 1) ? -(K / 2) : 1 - K / 2;
+    constexpr double SHIFT = (K & 1) ? 0.5 : 0.0;
+
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; ++s) {
+            mbar_init(&hdr->full[s], 1);
+            mbar_init(&hdr->empty[s], NTHREADS / 32);
+        }
+        hdr->kb = INT_MAX;
+        hdr->ke = INT_MIN;
+        hdr->bad = 0;
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    // ---- prologue: pixel records, CTA pulse range, corner positions ----------------
+    PixState st[PX];
+    bool in_grid[PX];
+    long long gidx[PX];
+    {
+        const int lrow = tid / (TILE_RG / PX);
+        const int lcol = (tid % (TILE_RG / PX)) * PX;
+        const int last_row = min(TILE_AZ, P.out_lines - line0) - 1;
+        const int last_col = min(TILE_RG, P.out_width - col0) - 1;
+        int kmin = INT_MAX, kmax = INT_MIN;
+        bool bad = false;
+#pragma unroll
+        for (int p = 0; p < PX; ++p) {
+            const int jj = line0 + lrow, ii = col0 + lcol + p;
+            in_grid[p] = (jj < P.out_lines) && (ii < P.out_width);
+            const int jc = min(jj, P.out_lines - 1), ic = min(ii, P.out_width - 1);
+            gidx[p] = (long long) jc * P.out_width + ic;
+            const PixelRec r = pix[gidx[p]];
+            if (r.kstart < 0) bad = true;
+            st[p].x = r.x; st[p].y = r.y; st[p].z = r.z;
+            st[p].xx = r.x * r.x + r.y * r.y + r.z * r.z;
+            const double t0cyc = P.fc * r.tau_atm;
+            st[p].upix = fma(t0cyc, P.G, SHIFT - P.U0);
+            st[p].mphase = MAGIC + t0cyc;
+            st[p].kstart = in_grid[p] ? max(r.kstart, P.k_begin) : 0;
+            st[p].kstop = in_grid[p] ? min(r.kstop, P.k_end) : 0;
+            st[p].accr = st[p].acci = 0.f;
+            if (st[p].kstop > st[p].kstart) {
+                kmin = min(kmin, st[p].kstart);
+                kmax = max(kmax, st[p].kstop);
+            }
+            // the four corner pixels of the (grid-clipped) tile publish their position
+            const int lc = lcol + p;
+            const bool top = lrow == 0, bot = lrow == last_row;
+            const bool lef = lc == 0, rig = lc == last_col;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const bool rsel = (c & 2) ? bot : top, csel = (c & 1) ? rig : lef;
+                if (rsel && csel) {
+                    hdr->corner[c][0] = r.x; hdr->corner[c][1] = r.y; hdr->corner[c][2] = r.z;
+                    hdr->corner[c][3] = t0cyc;
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+            kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+        }
+        const bool anybad = __any_sync(0xffffffffu, bad);
+        if (lane == 0) {
+            if (kmin != INT_MAX) atomicMin(&hdr->kb, kmin);
+            if (kmax != INT_MIN) atomicMax(&hdr->ke, kmax);
+            if (anybad) hdr->bad = 1;
+        }
+    }
+    __syncthreads();
+    const int kb = hdr->kb, ke = hdr->ke;
+    if (hdr->bad) {
+        if (tid == 0) tile_generic[blockIdx.x] = 1;
+        return;
+    }
+    if (kb >= ke) return; // nothing to integrate in this launch
+    const int ntiles = (ke - kb + TK - 1) / TK;
+
+    // Producer role (warp 0, all lanes converge here): stage pulse tile n.
+    auto produce = [&](int n) {
+        const int s = n % NSTAGE;
+        if (n >= NSTAGE) mbar_wait(&hdr->empty[s], ((n / NSTAGE) - 1) & 1);
+        const int kfirst = kb + n * TK;
+        const int klast = min(kfirst + TK - 1, P.n_pulses - 1);
+        // range window from the 4 corner pixels at the first/last pulse of the tile
+        double u = 0.;
+        if (lane < 8) {
+            const PulseRec r = pulse[(lane < 4) ? kfirst : klast];
+            u = sample_coord(hdr->corner[lane & 3], r, P.G, P.U0);
+        }
+        double umin = (lane < 8) ? u : 1e300, umax = (lane < 8) ? u : -1e300;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            umin = fmin(umin, __shfl_xor_sync(0xffffffffu, umin, o));
+            umax = fmax(umax, __shfl_xor_sync(0xffffffffu, umax, o));
+        }
+        if (lane == 0) {
+            int wlo = (int) floor(umin) - K / 2 - 3;
+            wlo &= ~1; // even: keeps LDS.128 parity == sample-index parity
+            const int whi = (int) ceil(umax) + K / 2 + 6;
+            if (!(umin == umin) || whi - wlo > P.W) status->window_overflow = 1;
+            hdr->winlo[s] = wlo;
+            unsigned char* sp = stage0 + (size_t) s * sbytes;
+            const uint32_t bytes = (uint32_t) ((size_t) TK * P.W * sizeof(float2) +
+                                               (size_t) TK * sizeof(PulseRec));
+            mbar_arrive_expect_tx(&hdr->full[s], bytes);
+            tma_load_2d(sp, &rc_map, wlo, kfirst - P.rc_k0, &hdr->full[s]);
+            bulk_load_1d(sp + (size_t) TK * P.W * sizeof(float2), pulse + kfirst,
+                         (uint32_t) (TK * sizeof(PulseRec)), &hdr->full[s]);
+        }
+        __syncwarp();
+    };
+    if (warp == 0) {
+        for (int n = 0; n < NSTAGE - 1 && n < ntiles; ++n) produce(n);
+    }
+
+    // initial range state: exact sqrt at the two pulses before kb (linear extrapolation
+    // when kb < 2), so the predictor 2*s1 - s2 starts within a second difference of truth.
+    {
+        const int ka = max(kb - 2, 0);
+        const PulseRec ra = pulse[ka], rb = pulse[min(ka + 1, P.n_pulses - 1)];
+#pragma unroll
+        for (int p = 0; p < PX; ++p) {
+            const double r2a = fma(st[p].x, ra.m2px, fma(st[p].y, ra.m2py, fma(st[p].z, ra.m2pz, st[p].xx + ra.pp)));
+            const double r2b = fma(st[p].x, rb.m2px, fma(st[p].y, rb.m2py, fma(st[p].z, rb.m2pz, st[p].xx + rb.pp)));
+            const double sa = sqrt(r2a), sb = sqrt(r2b);
+            const double slope = sb - sa;
+            st[p].s2 = fma(slope, (double) (kb - 2 - ka), sa);
+            st[p].s1 = fma(slope, (double) (kb - 1 - ka), sa);
+            st[p].yh = 0.5 / sa;
+        }
+    }
+    // FP64 running sums live in shared memory (one private slot per thread)
+    double* accd = reinterpret_cast<double*>(smem_raw + HEADER_BYTES + NSTAGE * sbytes) + tid * (2 * PX);
+#pragma unroll
+    for (int i = 0; i < 2 * PX; ++i) accd[i] = 0.0;
+    int overflow = 0;
+    const float TWO_PI = 6.28318530717958647692f, THREE_PI = 9.42477796076937971538f;
+
+    for (int n = 0; n < ntiles; ++n) {
+        if (warp == 0 && n + NSTAGE - 1 < ntiles) produce(n + NSTAGE - 1);
+        const int s = n % NSTAGE;
+        mbar_wait(&hdr->full[s], (n / NSTAGE) & 1);
+        const unsigned char* sp = stage0 + (size_t) s * sbytes;
+        const float2* lines = reinterpret_cast<const float2*>(sp);
+        const PulseRec* prec = reinterpret_cast<const PulseRec*>(sp + (size_t) TK * P.W * sizeof(float2));
+        // index constant: j0 = (mantissa >> 23) - CONST  (see MAGIC)
+        const unsigned jconst = 0x80000000u + 0x10000000u + (unsigned) hdr->winlo[s] - (unsigned) LOWOFF;
+        const int kfirst = kb + n * TK;
+        const unsigned jmax = (unsigned) (P.W - (K + 3));
+
+#pragma unroll 1
+        for (int kk = 0; kk < TK; ++kk) {
+            const PulseRec pr = prec[kk];
+            const int k = kfirst + kk;
+            float f[PX], cs[PX], sn[PX];
+            unsigned j0[PX];
+            bool clamped[PX];
+#pragma unroll
+            for (int p = 0; p < PX; ++p) {
+                PixState& q = st[p];
+                const double r2 = fma(q.x, pr.m2px, fma(q.y, pr.m2py, fma(q.z, pr.m2pz, q.xx + pr.pp)));
+                const double spred = fma(2.0, q.s1, -q.s2);
+                const double e = fma(-spred, spred, r2);
+                const double sv = fma(e, q.yh, spred);
+                q.s2 = q.s1;
+                q.s1 = sv;
+                const double tgeo = fma(pr.Cs, sv, fma(q.x, pr.vBx, fma(q.y, pr.vBy, fma(q.z, pr.vBz, pr.E))));
+                const double mu = fma(tgeo, P.G, q.upix) + MAGIC;
+                const double mt = tgeo + q.mphase;
+                const unsigned ulo = (unsigned) __double2loint(mu), uhi = (unsigned) __double2hiint(mu);
+                f[p] = __uint_as_float((ulo & 0x007FFFFFu) | 0x3F800000u) - 1.5f;
+                const unsigned jj = __funnelshift_r(ulo, uhi, 23) - jconst;
+                clamped[p] = jj > jmax;
+                j0[p] = min(jj, jmax);
+                const unsigned tlo = (unsigned) __double2loint(mt);
+                const float v = __uint_as_float((tlo & 0x007FFFFFu) | 0x3F800000u);
+                const float ang = fmaf(v, TWO_PI, -THREE_PI); // 2*pi*(frac - 0.5)
+                // cos/sin(2 pi frac) = -cos/-sin(ang); the sign is applied at the flush
+                cs[p] = __cosf(ang);
+                sn[p] = __sinf(ang);
+            }
+            const float2* line = lines + (size_t) kk * P.W;
+            float w0[K], w1[K];
+            Weights<K, D>::eval(f[0], w0);
+            Weights<K, D>::eval(f[1], w1);
+            float ar0 = 0.f, ai0 = 0.f, ar1 = 0.f, ai1 = 0.f;
+            if (j0[1] == j0[0] + 1) {
+                // shared register window: K+1 samples (+1 when the start is odd)
+                const unsigned base = j0[0] & ~1u;
+                constexpr int NV = (K + 3) / 2; // float4 loads covering K+2 samples
+                float4 v4[NV];
+                const float4* src = reinterpret_cast<const float4*>(line + base);
+#pragma unroll
+                for (int i = 0; i < NV; ++i) v4[i] = src[i];
+                const float2* sm = reinterpret_cast<const float2*>(v4);
+                if (j0[0] & 1u) {
+#pragma unroll
+                    for (int m = 0; m < K; ++m) {
+                        ar0 = fmaf(w0[m], sm[m + 1].x, ar0);
+                        ai0 = fmaf(w0[m], sm[m + 1].y, ai0);
+                        ar1 = fmaf(w1[m], sm[m + 2].x, ar1);
+                        ai1 = fmaf(w1[m], sm[m + 2].y, ai1);
+                    }
+                } else {
+#pragma unroll
+                    for (int m = 0; m < K; ++m) {
+                        ar0 = fmaf(w0[m], sm[m].x, ar0);
+                        ai0 = fmaf(w0[m], sm[m].y, ai0);
+                        ar1 = fmaf(w1[m], sm[m + 1].x, ar1);
+                        ai1 = fmaf(w1[m], sm[m + 1].y, ai1);
+                    }
+                }
+            } else {
+                // general spacing: independent windows
+#pragma unroll
+                for (int m = 0; m < K; ++m) {
+                    const float2 a = line[j0[0] + m], b = line[j0[1] + m];
+                    ar0 = fmaf(w0[m], a.x, ar0);
+                    ai0 = fmaf(w0[m], a.y, ai0);
+                    ar1 = fmaf(w1[m], b.x, ar1);
+                    ai1 = fmaf(w1[m], b.y, ai1);
+                }
+            }
+            if (k >= st[0].kstart && k < st[0].kstop) {
+                st[0].accr = fmaf(ar0, cs[0], fmaf(-ai0, sn[0], st[0].accr));
+                st[0].acci = fmaf(ar0, sn[0], fmaf(ai0, cs[0], st[0].acci));
+                if (clamped[0]) overflow = 1;
+            }
+            if (k >= st[1].kstart && k < st[1].kstop) {
+                st[1].accr = fmaf(ar1, cs[1], fmaf(-ai1, sn[1], st[1].accr));
+                st[1].acci = fmaf(ar1, sn[1], fmaf(ai1, cs[1], st[1].acci));
+                if (clamped[1]) overflow = 1;
+            }
+        }
+        // pulse tile done: fold FP32 partials into FP64, release the stage
+#pragma unroll
+        for (int p = 0; p < PX; ++p) {
+            accd[2 * p] -= (double) st[p].accr; // minus: see the half-cycle shift above
+            accd[2 * p + 1] -= (double) st[p].acci;
+            st[p].accr = st[p].acci = 0.f;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&hdr->empty[s]);
+    }
+#pragma unroll
+    for (int p = 0; p < PX; ++p) {
+        if (in_grid[p]) {
+            double2 a = acc[gidx[p]];
+            a.x += accd[2 * p];
+            a.y += accd[2 * p + 1];
+            acc[gidx[p]] = a;
+        }
+    }
+    if (overflow) status->window_overflow = 1;
+}
+
+// ---- host side: polynomial fit of the tap weights ---------------------------------------
+
+struct FitResult {
+    bool ok;
+    int K, D;
+    double max_err;
+    float even[MAX_TAPS / 2 + 1][MAX_COEF / 2];
+    float odd[MAX_TAPS / 2 + 1][MAX_COEF / 2];
+};
+
+// least squares fit of y(g), g in [-1,1], by Chebyshev-node sampling + normal equations in a
+// Chebyshev basis (well conditioned), converted to monomials in f = g/2.
+static void fit_tap(const DevKernel& k, double cm, int D, double* mono /*[D+1] in f*/)
+{
+    const int N = 64;
+    std::vector<double> g(N), y(N);
+    for (int j = 0; j < N; ++j) {
+        g[j] = std::cos(M_PI * (j + 0.5) / N);
+        y[j] = (double) kernel_eval(k, cm - 0.5 * g[j]);
+    }
+    // discrete Chebyshev transform (nodes are Chebyshev zeros -> orthogonal)
+    std::vector<double> a(D + 1);
+    for (int i = 0; i <= D; ++i) {
+        double sum = 0;
+        for (int j = 0; j < N; ++j) sum += y[j] * std::cos(i * M_PI * (j + 0.5) / N);
+        a[i] = (i == 0 ? 1.0 : 2.0) * sum / N;
+    }
+    // Chebyshev -> monomial in g
+    std::vector<std::vector<double>> T(D + 1, std::vector<double>(D + 1, 0.0));
+    T[0][0] = 1;
+    if (D >= 1) T[1][1] = 1;
+    for (int i = 2; i <= D; ++i)
+        for (int p = 0; p <= i; ++p)
+            T[i][p] = (p > 0 ? 2 * T[i - 1][p - 1] : 0.0) - T[i - 2][p];
+    for (int p = 0; p <= D; ++p) {
+        double c = 0;
+        for (int i = p; i <= D; ++i) c += a[i] * T[i][p];
+        mono[p] = c * std::pow(2.0, p); // g = 2 f
+    }
+}
+
+static FitResult fit_kernel(const DevKernel& k, double tol)
+{
+    FitResult R;
+    std::memset(&R, 0, sizeof(R));
+    R.K = k.taps;
+    R.D = (k.taps & 1) ? 6 : 7;
+    const int K = R.K, D = R.D;
+    const int nh = (K + 1) / 2;
+    double worst = 0;
+    for (int m = 0; m < nh; ++m) {
+        const double cm = m - 0.5 * (K - 1);
+        double mono[MAX_COEF + 1] = {};
+        fit_tap(k, cm, D, mono);
+        // taps m and K-1-m are mirror images: symmetrise (w_m(f) = E + f O, w_{K-1-m} = E - f O)
+        double mono2[MAX_COEF + 1] = {};
+        if (2 * m != K - 1) {
+            fit_tap(k, -cm, D, mono2);
+            for (int p = 0; p <= D; ++p) {
+                const double mir = (p & 1) ? -mono2[p] : mono2[p];
+                mono[p] = 0.5 * (mono[p] + mir);
+            }
+        } else {
+            for (int p = 1; p <= D; p += 2) mono[p] = 0.0;
+        }
+        for (int p = 0; p <= D; ++p) {
+            if (p & 1) R.odd[m][p / 2] = (float) mono[p];
+            else R.even[m][p / 2] = (float) mono[p];
+        }
+        // residual of the float Horner evaluation against the caller's kernel
+        for (int j = 0; j <= 400; ++j) {
+            const float f = (float) (-0.5 + j / 400.0);
+            const float h = f * f;
+            const int NE = D / 2 + 1, NO = (D + 1) / 2;
+            float e = R.even[m][NE - 1];
+            for (int i = NE - 2; i >= 0; --i) e = fmaf(e, h, R.even[m][i]);
+            float o = R.odd[m][NO - 1];
+            for (int i = NO - 2; i >= 0; --i) o = fmaf(o, h, R.odd[m][i]);
+            const double wp = fmaf(f, o, e), wm = fmaf(-f, o, e);
+            worst = std::max(worst, std::fabs(wp - (double) kernel_eval(k, cm - (double) f)));
+            if (2 * m != K - 1)
+                worst = std::max(worst, std::fabs(wm - (double) kernel_eval(k, -cm - (double) f)));
+        }
+    }
+    R.max_err = worst;
+    R.ok = worst <= tol;
+    return R;
+}
+
+constexpr double FIT_TOL = 3e-5;
+
+static bool taps_supported(int K) { return K == 8 || K == 9 || K == 16 || K == 32; }
+
+bool fast_supported(const DevKernel& hk, char* why, size_t why_len)
+{
+    if (!taps_supported(hk.taps)) {
+        snprintf(why, why_len, "tap count %d has no fast instantiation (8, 9, 16, 32)", hk.taps);
+        return false;
+    }
+    if (hk.kind == I3B_KERNEL_BARTLETT || hk.kind == I3B_KERNEL_LINEAR) {
+        snprintf(why, why_len, "piecewise-linear kernel is not polynomial per tap");
+        return false;
+    }
+    const FitResult R = fit_kernel(hk, FIT_TOL);
+    if (!R.ok) {
+        snprintf(why, why_len, "per-tap polynomial fit residual %.2e > %.1e", R.max_err, FIT_TOL);
+        return false;
+    }
+    return true;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) ==
+                    cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn) p;
+    }
+    return fn;
+}
+
+template<int K, int D>
+static int launch_inst(const CUtensorMap& map, const FastParams& FP, const PixelRec* pix,
+                       const PulseRec* pulse, double2* acc, unsigned char* tile_generic,
+                       DevStatus* status, size_t smem, cudaStream_t s)
+{
+    auto kern = accumulate_fast_kernel<K, D>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (e != cudaSuccess) return (int) e;
+    const unsigned grid = (unsigned) (FP.tiles_rg * FP.tiles_az);
+    kern<<<grid, NTHREADS, smem, s>>>(map, FP, pix, pulse, acc, tile_generic, status);
+    return (int) cudaGetLastError();
+}
+
+// Returns 0 on success, >0 a cudaError_t, -1 if the configuration is unsupported
+// (caller falls back to the generic kernel).  `tile_generic` (one byte per tile, zeroed by
+// the caller) is set for tiles that hold failed pixels; the caller runs the generic kernel
+// on those tiles.
+int launch_accumulate_fast(const AccumParams& P, const DevKernel& hk, const PixelRec* pix,
+                           const PulseRec* pulse, const float2* rc, double2* acc,
+                           unsigned char* tile_generic, DevStatus* status, cudaStream_t s)
+{
+    const int rc_rows = P.rc_rows, n_pulses = P.n_pulses;
+    const double out_in_spacing_ratio = P.spacing_ratio;
+    // the magic-number splits need |fc*tau| and |u| below 2^28
+    if (P.fc * (P.swst + (P.nr + 64) * P.dtau) > 2.6e8 || P.nr > (1 << 27)) return -1;
+    const FitResult R = fit_kernel(hk, FIT_TOL);
+    if (!R.ok || !taps_supported(hk.taps)) return -1;
+    const int K = hk.taps;
+    int W = (int) std::ceil(TILE_RG * std::fabs(out_in_spacing_ratio) * 1.002) + K + 16;
+    W = (W + 1) & ~1;
+    if (W > 256) return -1;
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return -1;
+    CUtensorMap map;
+    const cuuint64_t gdim[2] = {(cuuint64_t) P.nr, (cuuint64_t) rc_rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t) P.rc_pitch * sizeof(float2)};
+    const cuuint32_t box[2] = {(cuuint32_t) W, (cuuint32_t) TK};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult cr = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*) rc, gdim, gstride, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return -1;
+
+    cudaError_t e;
+    e = cudaMemcpyToSymbolAsync(c_even, R.even, sizeof(R.even), 0, cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) return (int) e;
+    e = cudaMemcpyToSymbolAsync(c_odd, R.odd, sizeof(R.odd), 0, cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) return (int) e;
+
+    FastParams FP;
+    FP.npix = P.npix;
+    FP.out_lines = P.out_lines;
+    FP.out_width = P.out_width;
+    FP.nr = P.nr;
+    FP.rc_k0 = P.rc_k0;
+    FP.rc_rows = rc_rows;
+    FP.k_begin = P.k_begin;
+    FP.k_end = P.k_end;
+    FP.n_pulses = n_pulses;
+    FP.W = W;
+    FP.tiles_rg = (P.out_width + TILE_RG - 1) / TILE_RG;
+    FP.tiles_az = (P.out_lines + TILE_AZ - 1) / TILE_AZ;
+    FP.G = 1.0 / (P.fc * P.dtau);
+    FP.U0 = P.swst / P.dtau;
+    FP.fc = P.fc;
+    const size_t smem = HEADER_BYTES + NSTAGE * stage_bytes(W) + (size_t) NTHREADS * 2 * PX * sizeof(double);
+    switch (K) {
+    case 8: return launch_inst<8, 7>(map, FP, pix, pulse, acc, tile_generic, status, smem, s);
+    case 9: return launch_inst<9, 6>(map, FP, pix, pulse, acc, tile_generic, status, smem, s);
+    case 16: return launch_inst<16, 7>(map, FP, pix, pulse, acc, tile_generic, status, smem, s);
+    case 32: return launch_inst<32, 7>(map, FP, pix, pulse, acc, tile_generic, status, smem, s);
+    default: return -1;
+    }
+}
+
+int fast_tiles(int out_lines, int out_width)
+{
+    return ((out_width + TILE_RG - 1) / TILE_RG) * ((out_lines + TILE_AZ - 1) / TILE_AZ);
+}
+
+void fast_tile_shape(int* tile_az, int* tile_rg)
+{
+    *tile_az = TILE_AZ;
+    *tile_rg = TILE_RG;
+}
+
+} // namespace i3b

@@ -1,0 +1,751 @@
+// C-ABI of the B200 TDBP backend (include/isce3_b200_backproject.h) and its host driver:
+// argument validation, device staging, shard-per-GPU execution, statistics.
+//
+// Replaces the host sequence of isce3::cuda::focus::backproject
+// (cxx/isce3/cuda/focus/Backproject.cu:468-754): 8 synchronous kernels + a blocking
+// cudaMemcpy per pulse batch there; here one fused target-solve kernel, and pulse slabs
+// uploaded on a copy stream while the accumulation kernel of the previous slab runs.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "launch.h"
+
+namespace i3b {
+
+struct ApiError : std::runtime_error {
+    int code;
+    ApiError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            char buf__[512];                                                                  \
+            snprintf(buf__, sizeof buf__, "%s failed: %s (%s:%d)", #call,                     \
+                     cudaGetErrorString(e__), __FILE__, __LINE__);                            \
+            throw ApiError(e__ == cudaErrorNoDevice || e__ == cudaErrorInsufficientDriver     \
+                                   ? I3B_EXC_NO_DEVICE                                        \
+                                   : I3B_EXC_CUDA_ERROR,                                      \
+                           buf__);                                                            \
+        }                                                                                     \
+    } while (0)
+
+static thread_local std::string g_last_error;
+static thread_local I3B_Stats g_last_stats;
+
+template<typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    void alloc(size_t count)
+    {
+        release();
+        n = count;
+        if (count) CK(cudaMalloc(&p, count * sizeof(T)));
+    }
+    void upload(const T* src, size_t count, cudaStream_t s)
+    {
+        alloc(count);
+        if (count) CK(cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    }
+};
+
+struct Event {
+    cudaEvent_t e = nullptr;
+    Event() { CK(cudaEventCreate(&e)); }
+    ~Event() { if (e) cudaEventDestroy(e); }
+    void record(cudaStream_t s) { CK(cudaEventRecord(e, s)); }
+};
+
+static float elapsed(const Event& a, const Event& b)
+{
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, a.e, b.e));
+    return ms;
+}
+
+// Deep host copy of the caller's descriptors (a plan may outlive the caller's arrays).
+struct HostScene {
+    I3B_BackprojectArgs a;
+    std::vector<double> out_pos, out_vel, in_pos, in_vel, out_dop, in_dop;
+    std::vector<float> dem, kdata;
+    std::vector<int> devices;
+};
+
+static void validate(const I3B_BackprojectArgs& a)
+{
+    auto bad = [](const std::string& m) { throw ApiError(I3B_EXC_INVALID_ARGUMENT, m); };
+    if (a.abi_version != I3B_ABI_VERSION) bad("ABI version mismatch");
+    if (!a.in) bad("input signal data is null");
+    if (!(a.dry_tropo_model == I3B_TROPO_NODELAY || a.dry_tropo_model == I3B_TROPO_TSX))
+        bad("unexpected dry troposphere model"); // Backproject.cpp:78-83
+    if (a.batch < 1) throw ApiError(I3B_EXC_DOMAIN_ERROR, "batch size must be > 0");
+    const I3B_RadarGeometry &og = a.out_geometry, &ig = a.in_geometry;
+    if (og.ref_epoch_sec != ig.ref_epoch_sec || og.ref_epoch_frac != ig.ref_epoch_frac)
+        throw ApiError(I3B_EXC_RUNTIME_ERROR,
+                       "input reference epoch must match output reference epoch"); // :88-92
+    for (const I3B_RadarGeometry* g : {&og, &ig}) {
+        if (g->grid.length < 0 || g->grid.width < 0) bad("negative grid dimension");
+        if (g->grid.length > INT_MAX) throw ApiError(I3B_EXC_OVERFLOW_ERROR, "grid length exceeds max int");
+        if (g->grid.width > INT_MAX) throw ApiError(I3B_EXC_OVERFLOW_ERROR, "grid width exceeds max int");
+        if (!(g->grid.prf > 0)) bad("PRF must be positive");
+        if (g->orbit.n < 2 || !g->orbit.pos || !g->orbit.vel) bad("orbit needs state vectors");
+        if (g->orbit.method != I3B_ORBIT_HERMITE && g->orbit.method != I3B_ORBIT_LEGENDRE)
+            bad("unknown orbit interpolation method");
+        if (g->grid.look_side != I3B_LOOK_LEFT && g->grid.look_side != I3B_LOOK_RIGHT)
+            bad("invalid look side");
+        if (g->doppler.have_data) {
+            if (!g->doppler.data || g->doppler.length < 1 || g->doppler.width < 1)
+                bad("Doppler LUT has no data");
+            if (g->doppler.method == I3B_INTERP_SINC) bad("sinc LUT2d interpolation is not supported");
+        }
+    }
+    if (a.dem.have_raster) {
+        if (!a.dem.data || a.dem.length < 4 || a.dem.width < 4) bad("DEM raster too small");
+        if (a.dem.epsg != 4326) bad("raster DEMs are supported for EPSG:4326 only");
+        if (a.dem.method == I3B_INTERP_SINC) bad("sinc DEM interpolation is not supported");
+    }
+    if (!(a.fc > 0) || !(a.ds > 0)) bad("fc and ds must be positive");
+    const I3B_Kernel& k = a.kernel;
+    switch (k.kind) {
+    case I3B_KERNEL_BARTLETT:
+    case I3B_KERNEL_LINEAR: break;
+    case I3B_KERNEL_KNAB:
+        if (!(k.bandwidth > 0.0 && k.bandwidth < 1.0)) throw ApiError(I3B_EXC_RUNTIME_ERROR, "Require 0 < bandwidth < 1");
+        break;
+    case I3B_KERNEL_TABULATED:
+        if (!k.data || k.n < 2) throw ApiError(I3B_EXC_INVALID_ARGUMENT, "Require table size >= 2.");
+        break;
+    case I3B_KERNEL_CHEBY:
+        if (!k.data || k.n < 1) throw ApiError(I3B_EXC_INVALID_ARGUMENT, "Need at least one coefficient.");
+        break;
+    default: throw ApiError(I3B_EXC_RUNTIME_ERROR, "not implemented"); // Backproject.cu:750-752
+    }
+    const double width = k.kind == I3B_KERNEL_LINEAR ? 2.0 : k.width;
+    if (!(width > 0) || std::ceil(width) > 1024) bad("unsupported kernel width");
+    if (a.n_devices < 0 || (a.n_devices > 0 && !a.devices)) bad("bad device list");
+    if ((a.flags & I3B_FLAG_DEVICE_POINTERS) && a.n_devices > 1)
+        bad("device-pointer mode is single-device only");
+}
+
+static void copy_geometry(const I3B_RadarGeometry& g, std::vector<double>& pos,
+                          std::vector<double>& vel, std::vector<double>& dop, I3B_RadarGeometry& out)
+{
+    out = g;
+    pos.assign(g.orbit.pos, g.orbit.pos + 3 * (size_t) g.orbit.n);
+    vel.assign(g.orbit.vel, g.orbit.vel + 3 * (size_t) g.orbit.n);
+    out.orbit.pos = pos.data();
+    out.orbit.vel = vel.data();
+    if (g.doppler.have_data) {
+        dop.assign(g.doppler.data, g.doppler.data + (size_t) g.doppler.length * g.doppler.width);
+        out.doppler.data = dop.data();
+    }
+}
+
+static DevKernel make_kernel(const I3B_Kernel& k, const float* data)
+{
+    DevKernel d;
+    std::memset(&d, 0, sizeof d);
+    d.kind = k.kind;
+    d.n = k.n;
+    const double width = k.kind == I3B_KERNEL_LINEAR ? 2.0 : k.width; // core/Kernels.h:51
+    d.halfwidth = std::fabs(width / 2.0);
+    d.taps = (int) std::ceil(d.halfwidth * 2);
+    d.bandwidth = k.bandwidth;
+    if (k.kind == I3B_KERNEL_TABULATED) {
+        d.imax = k.n - 2;
+        const double dx = d.halfwidth / (k.n - 1.0);
+        d.one_dx = (float) (1.0 / dx);
+    } else if (k.kind == I3B_KERNEL_CHEBY) {
+        d.cheb_scale = (float) (4.0 / width);
+    }
+    d.data = data;
+    return d;
+}
+
+// Everything one GPU holds for its azimuth block of the output grid.
+struct Shard {
+    int device = 0;
+    int line0 = 0, nlines = 0;
+    cudaStream_t compute = nullptr, copy = nullptr;
+    DevBuf<double> out_pos, out_vel, in_pos, in_vel, out_dop, in_dop, pv;
+    DevBuf<float> dem, kdata, height;
+    DevBuf<PulseRec> pulse;
+    DevBuf<PixelRec> pix;
+    DevBuf<double2> acc;
+    DevBuf<float2> out, rc;
+    DevBuf<DevStatus> status;
+    DevBuf<unsigned char> tile_mask;
+    const float2* rc_dev = nullptr; // staged lines (or the caller's device pointer)
+    int rc_pitch = 0, rc_k0 = 0, rc_rows = 0;
+    bool rc_resident = false;
+    SolveParams sp;
+    AccumParams ap;
+    DevKernel host_kernel;
+    bool use_fast = false;
+    I3B_Stats stats;
+    int status_code = 0;
+    std::string error;
+
+    ~Shard()
+    {
+        if (compute || copy) cudaSetDevice(device);
+        if (compute) cudaStreamDestroy(compute);
+        if (copy) cudaStreamDestroy(copy);
+    }
+};
+
+} // namespace i3b
+
+using namespace i3b;
+
+struct I3B_Plan {
+    HostScene hs;
+    std::vector<std::unique_ptr<Shard>> shards;
+    bool solved = false;
+};
+
+namespace i3b {
+
+static void shard_setup(const HostScene& hs, Shard& sh)
+{
+    const I3B_BackprojectArgs& a = hs.a;
+    CK(cudaSetDevice(sh.device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, sh.device));
+    if (prop.major < 10)
+        throw ApiError(I3B_EXC_NO_DEVICE,
+                       std::string("device ") + prop.name + " is not sm_100-class; isce3_b200 has no fallback path");
+    CK(cudaStreamCreateWithFlags(&sh.compute, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&sh.copy, cudaStreamNonBlocking));
+    cudaStream_t s = sh.compute;
+    const I3B_RadarGeometry &og = a.out_geometry, &ig = a.in_geometry;
+    sh.out_pos.upload(og.orbit.pos, 3 * (size_t) og.orbit.n, s);
+    sh.out_vel.upload(og.orbit.vel, 3 * (size_t) og.orbit.n, s);
+    sh.in_pos.upload(ig.orbit.pos, 3 * (size_t) ig.orbit.n, s);
+    sh.in_vel.upload(ig.orbit.vel, 3 * (size_t) ig.orbit.n, s);
+    if (og.doppler.have_data) sh.out_dop.upload(og.doppler.data, (size_t) og.doppler.length * og.doppler.width, s);
+    if (ig.doppler.have_data) sh.in_dop.upload(ig.doppler.data, (size_t) ig.doppler.length * ig.doppler.width, s);
+    if (a.dem.have_raster) sh.dem.upload(a.dem.data, (size_t) a.dem.length * a.dem.width, s);
+    if (a.kernel.data && a.kernel.n > 0) sh.kdata.upload(a.kernel.data, (size_t) a.kernel.n, s);
+
+    auto dev_orbit = [](const I3B_Orbit& o, const double* p, const double* v) {
+        return DevOrbit {o.t0, o.dt, o.n, o.method, p, v};
+    };
+    auto dev_lut = [](const I3B_LUT2d& l, const double* d) {
+        DevLUT2d r;
+        r.have_data = l.have_data; r.bounds_error = l.bounds_error; r.method = l.method;
+        r.length = (int) l.length; r.width = (int) l.width;
+        r.ref_value = l.ref_value; r.xstart = l.xstart; r.ystart = l.ystart; r.dx = l.dx; r.dy = l.dy;
+        r.data = d;
+        return r;
+    };
+    SolveParams& P = sh.sp;
+    P.out_time = Linspace {og.grid.sensing_start, 1.0 / og.grid.prf, (int) og.grid.length};
+    P.out_range = Linspace {og.grid.starting_range, og.grid.range_pixel_spacing, (int) og.grid.width};
+    P.in_time = Linspace {ig.grid.sensing_start, 1.0 / ig.grid.prf, (int) ig.grid.length};
+    P.out_orbit = dev_orbit(og.orbit, sh.out_pos.p, sh.out_vel.p);
+    P.in_orbit = dev_orbit(ig.orbit, sh.in_pos.p, sh.in_vel.p);
+    P.out_doppler = dev_lut(og.doppler, sh.out_dop.p);
+    P.in_doppler = dev_lut(ig.doppler, sh.in_dop.p);
+    P.dem.have_raster = a.dem.have_raster; P.dem.epsg = a.dem.epsg; P.dem.method = a.dem.method;
+    P.dem.length = (int) a.dem.length; P.dem.width = (int) a.dem.width;
+    P.dem.ref_height = a.dem.ref_height; P.dem.xstart = a.dem.xstart; P.dem.ystart = a.dem.ystart;
+    P.dem.dx = a.dem.dx; P.dem.dy = a.dem.dy; P.dem.data = sh.dem.p;
+    P.r2g = a.rdr2geo;
+    P.g2r = a.geo2rdr;
+    P.wvl = kC / a.fc; // Backproject.cpp:119: wavelength from fc, not from the grid
+    P.ds = a.ds;
+    P.out_side = og.grid.look_side;
+    P.in_side = ig.grid.look_side;
+    P.tropo = a.dry_tropo_model;
+    P.line0 = sh.line0;
+    P.out_lines = sh.nlines;
+    P.out_width = (int) og.grid.width;
+
+    const size_t npix = (size_t) sh.nlines * og.grid.width;
+    const int n_pulses = (int) ig.grid.length;
+    sh.pulse.alloc((size_t) n_pulses + kPulseTablePad);
+    CK(cudaMemsetAsync(sh.pulse.p, 0, sh.pulse.n * sizeof(PulseRec), s));
+    sh.pv.alloc((size_t) 6 * std::max(n_pulses, 1));
+    sh.status.alloc(1);
+    sh.pix.alloc(npix);
+    sh.acc.alloc(npix);
+    sh.out.alloc(npix);
+    sh.height.alloc(npix);
+    sh.tile_mask.alloc((size_t) std::max(fast_tiles(sh.nlines, (int) og.grid.width), 1));
+
+    AccumParams& A = sh.ap;
+    std::memset(&A, 0, sizeof A);
+    A.npix = (long long) npix;
+    A.out_lines = sh.nlines;
+    A.out_width = (int) og.grid.width;
+    A.nr = (int) ig.grid.width;
+    A.n_pulses = n_pulses;
+    A.fc = a.fc;
+    A.swst = 2. * ig.grid.starting_range / kC;       // Backproject.cpp:109-112
+    A.dtau = 2. * ig.grid.range_pixel_spacing / kC;
+    A.spacing_ratio = og.grid.range_pixel_spacing / ig.grid.range_pixel_spacing;
+    A.kernel = make_kernel(a.kernel, sh.kdata.p);
+    fast_tile_shape(&A.tile_az, &A.tile_rg);
+    A.tiles_rg = (A.out_width + A.tile_rg - 1) / A.tile_rg;
+    sh.host_kernel = make_kernel(a.kernel, a.kernel.data);
+    char why[160] = "";
+    sh.use_fast = !(a.flags & I3B_FLAG_FORCE_GENERIC) && fast_supported(sh.host_kernel, why, sizeof why);
+    std::memset(&sh.stats, 0, sizeof sh.stats);
+    sh.stats.taps = A.kernel.taps;
+}
+
+// pulse table + per-pixel target solve; returns the soft/hard status
+static void shard_solve(const HostScene& hs, Shard& sh)
+{
+    CK(cudaSetDevice(sh.device));
+    cudaStream_t s = sh.compute;
+    DevStatus init;
+    std::memset(&init, 0, sizeof init);
+    init.kmin = INT_MAX;
+    init.kmax = INT_MIN;
+    CK(cudaMemcpyAsync(sh.status.p, &init, sizeof init, cudaMemcpyHostToDevice, s));
+    Event e0, e1;
+    e0.record(s);
+    launch_pulse_table(sh.sp.in_orbit, sh.sp.in_time, hs.a.fc, sh.pulse.p, sh.pv.p, sh.status.p, s);
+    CK(cudaGetLastError());
+    if (sh.ap.npix > 0) {
+        launch_target_solve(sh.sp, sh.pix.p, sh.height.p, sh.status.p, s);
+        CK(cudaGetLastError());
+    }
+    e1.record(s);
+    DevStatus st;
+    CK(cudaMemcpyAsync(&st, sh.status.p, sizeof st, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    sh.stats.ms_target_solve = elapsed(e0, e1);
+    sh.stats.total_launches += 2;
+    sh.stats.pixel_pulses = (double) st.pixel_pulses;
+    if (st.hard_error) throw ApiError(st.hard_error, "orbit interpolation outside of orbit domain");
+    sh.status_code = st.soft_error;
+    if (st.kmin == INT_MAX) { // no pixel integrates anything
+        sh.stats.pulse_first = sh.stats.pulse_last = 0;
+    } else {
+        sh.stats.pulse_first = st.kmin;
+        sh.stats.pulse_last = st.kmax;
+    }
+}
+
+// accumulate pulses [k0, k1) (must be staged) into acc
+static void shard_accumulate(Shard& sh, int k0, int k1, cudaStream_t s)
+{
+    AccumParams A = sh.ap;
+    A.rc_pitch = sh.rc_pitch;
+    A.rc_k0 = sh.rc_k0;
+    A.rc_rows = sh.rc_rows;
+    A.k_begin = k0;
+    A.k_end = k1;
+    A.tile_mask = nullptr;
+    bool done = false;
+    if (sh.use_fast) {
+        CK(cudaMemsetAsync(sh.tile_mask.p, 0, sh.tile_mask.n, s));
+        const int rc = launch_accumulate_fast(A, sh.host_kernel, sh.pix.p, sh.pulse.p, sh.rc_dev,
+                                              sh.acc.p, sh.tile_mask.p, sh.status.p, s);
+        if (rc > 0) CK((cudaError_t) rc);
+        if (rc == 0) {
+            done = true;
+            sh.stats.accumulate_launches += 1;
+            sh.stats.total_launches += 1;
+            // tiles holding failed pixels were skipped: generic kernel on just those
+            A.tile_mask = sh.tile_mask.p;
+            launch_accumulate_generic(A, sh.pix.p, sh.pv.p, sh.rc_dev, sh.acc.p, s);
+            CK(cudaGetLastError());
+            sh.stats.total_launches += 1;
+        } else {
+            sh.use_fast = false;
+        }
+    }
+    if (!done) {
+        A.tile_mask = nullptr;
+        launch_accumulate_generic(A, sh.pix.p, sh.pv.p, sh.rc_dev, sh.acc.p, s);
+        CK(cudaGetLastError());
+        sh.stats.accumulate_launches += 1;
+        sh.stats.total_launches += 1;
+    }
+}
+
+// Stage the needed pulses and integrate them, slab by slab: the copy of slab c+1 runs on the
+// copy stream while slab c is integrated on the compute stream.
+static void shard_run(const HostScene& hs, Shard& sh, bool resident_only)
+{
+    const I3B_BackprojectArgs& a = hs.a;
+    CK(cudaSetDevice(sh.device));
+    cudaStream_t s = sh.compute;
+    const int nr = sh.ap.nr;
+    const int kfirst = sh.stats.pulse_first, klast = sh.stats.pulse_last;
+    CK(cudaMemsetAsync(sh.acc.p, 0, sh.acc.n * sizeof(double2), s));
+    Event ea0, ea1;
+    double ms_h2d = 0.0;
+    if (klast > kfirst && sh.ap.npix > 0) {
+        const bool devptr = (a.flags & I3B_FLAG_DEVICE_POINTERS) != 0;
+        if (!sh.rc_resident) {
+            if (devptr && (nr % 2 == 0)) {
+                sh.rc_dev = reinterpret_cast<const float2*>(a.in);
+                sh.rc_pitch = nr;
+                sh.rc_k0 = 0;
+                sh.rc_rows = (int) a.in_geometry.grid.length;
+                sh.rc_resident = true;
+            } else {
+                sh.rc_pitch = (nr + 1) & ~1; // 16-byte line pitch (TMA global stride rule)
+                sh.rc_k0 = kfirst;
+                sh.rc_rows = klast - kfirst;
+                sh.rc.alloc((size_t) sh.rc_rows * sh.rc_pitch);
+                sh.rc_dev = sh.rc.p;
+                if (sh.rc_pitch != nr)
+                    CK(cudaMemsetAsync(sh.rc.p, 0, sh.rc.n * sizeof(float2), sh.copy));
+            }
+        }
+        ea0.record(s);
+        if (sh.rc_resident) {
+            shard_accumulate(sh, kfirst, klast, s);
+        } else {
+            const float2* in = reinterpret_cast<const float2*>(a.in);
+            const int slab = std::max(a.batch, 1);
+            std::vector<std::unique_ptr<Event>> landed;
+            const auto t0 = std::chrono::steady_clock::now();
+            for (int k = kfirst; k < klast; k += slab) {
+                const int rows = std::min(slab, klast - k);
+                CK(cudaMemcpy2DAsync(sh.rc.p + (size_t) (k - sh.rc_k0) * sh.rc_pitch,
+                                     (size_t) sh.rc_pitch * sizeof(float2), in + (size_t) k * nr,
+                                     (size_t) nr * sizeof(float2), (size_t) nr * sizeof(float2), rows,
+                                     devptr ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, sh.copy));
+                landed.emplace_back(new Event());
+                landed.back()->record(sh.copy);
+                CK(cudaStreamWaitEvent(s, landed.back()->e, 0));
+                sh.stats.h2d_bytes += (int64_t) rows * nr * (int64_t) sizeof(float2);
+                if (!resident_only) shard_accumulate(sh, k, k + rows, s);
+            }
+            CK(cudaStreamSynchronize(sh.copy));
+            ms_h2d = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            if (resident_only) sh.rc_resident = true;
+        }
+        ea1.record(s);
+    } else {
+        ea0.record(s);
+        ea1.record(s);
+    }
+    if (resident_only) {
+        CK(cudaStreamSynchronize(s));
+        sh.stats.ms_h2d = ms_h2d;
+        return;
+    }
+    launch_finalize(sh.ap.npix, sh.pix.p, sh.acc.p, sh.out.p, s);
+    CK(cudaGetLastError());
+    sh.stats.total_launches += 1;
+    DevStatus st;
+    CK(cudaMemcpyAsync(&st, sh.status.p, sizeof st, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    sh.stats.ms_accumulate = elapsed(ea0, ea1);
+    sh.stats.ms_h2d = ms_h2d;
+    sh.stats.used_fast_kernel = sh.use_fast ? 1 : 0;
+    if (st.window_overflow && sh.use_fast) {
+        // the staged range window was too small for some gather: redo with the generic kernel
+        sh.use_fast = false;
+        DevStatus clr = st;
+        clr.window_overflow = 0;
+        CK(cudaMemcpyAsync(sh.status.p, &clr, sizeof clr, cudaMemcpyHostToDevice, s));
+        CK(cudaMemsetAsync(sh.acc.p, 0, sh.acc.n * sizeof(double2), s));
+        Event eb0, eb1;
+        eb0.record(s);
+        shard_accumulate(sh, kfirst, klast, s);
+        eb1.record(s);
+        launch_finalize(sh.ap.npix, sh.pix.p, sh.acc.p, sh.out.p, s);
+        CK(cudaStreamSynchronize(s));
+        sh.stats.ms_accumulate += elapsed(eb0, eb1);
+        sh.stats.used_fast_kernel = 0;
+    }
+}
+
+static void shard_download(const HostScene& hs, Shard& sh, float* out, float* height)
+{
+    CK(cudaSetDevice(sh.device));
+    cudaStream_t s = sh.compute;
+    const size_t width = (size_t) hs.a.out_geometry.grid.width;
+    const size_t off = (size_t) sh.line0 * width;
+    const bool devptr = (hs.a.flags & I3B_FLAG_DEVICE_POINTERS) != 0;
+    const auto kind = devptr ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    Event e0, e1;
+    e0.record(s);
+    if (out && sh.ap.npix) {
+        CK(cudaMemcpyAsync(reinterpret_cast<float2*>(out) + off, sh.out.p, sh.out.n * sizeof(float2), kind, s));
+        sh.stats.d2h_bytes += (int64_t) (sh.out.n * sizeof(float2));
+    }
+    if (height && sh.ap.npix) {
+        CK(cudaMemcpyAsync(height + off, sh.height.p, sh.height.n * sizeof(float), kind, s));
+        sh.stats.d2h_bytes += (int64_t) (sh.height.n * sizeof(float));
+    }
+    e1.record(s);
+    CK(cudaStreamSynchronize(s));
+    sh.stats.ms_d2h = elapsed(e0, e1);
+}
+
+static std::unique_ptr<I3B_Plan> make_plan(const I3B_BackprojectArgs* args)
+{
+    if (!args) throw ApiError(I3B_EXC_INVALID_ARGUMENT, "null argument block");
+    validate(*args);
+    std::unique_ptr<I3B_Plan> plan(new I3B_Plan());
+    HostScene& hs = plan->hs;
+    hs.a = *args;
+    copy_geometry(args->out_geometry, hs.out_pos, hs.out_vel, hs.out_dop, hs.a.out_geometry);
+    copy_geometry(args->in_geometry, hs.in_pos, hs.in_vel, hs.in_dop, hs.a.in_geometry);
+    if (args->dem.have_raster) {
+        hs.dem.assign(args->dem.data, args->dem.data + (size_t) args->dem.length * args->dem.width);
+        hs.a.dem.data = hs.dem.data();
+    }
+    if (args->kernel.data && args->kernel.n > 0) {
+        hs.kdata.assign(args->kernel.data, args->kernel.data + args->kernel.n);
+        hs.a.kernel.data = hs.kdata.data();
+    }
+    int ndev_avail = 0;
+    {
+        cudaError_t e = cudaGetDeviceCount(&ndev_avail);
+        if (e != cudaSuccess || ndev_avail < 1)
+            throw ApiError(I3B_EXC_NO_DEVICE,
+                           std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                                   "); isce3_b200 has no CPU fallback");
+    }
+    if (args->n_devices > 0) hs.devices.assign(args->devices, args->devices + args->n_devices);
+    else {
+        int cur = 0;
+        CK(cudaGetDevice(&cur));
+        hs.devices.assign(1, cur);
+    }
+    for (int d : hs.devices)
+        if (d < 0 || d >= ndev_avail) throw ApiError(I3B_EXC_INVALID_ARGUMENT, "device ordinal out of range");
+    hs.a.devices = hs.devices.data();
+    hs.a.n_devices = (int) hs.devices.size();
+    // contiguous azimuth blocks, one per device
+    const int lines = (int) args->out_geometry.grid.length;
+    const int nsh = (int) std::min<size_t>(hs.devices.size(), (size_t) std::max(lines, 1));
+    int line = 0;
+    for (int i = 0; i < nsh; ++i) {
+        const int n = lines / nsh + (i < lines % nsh ? 1 : 0);
+        std::unique_ptr<Shard> sh(new Shard());
+        sh->device = hs.devices[i];
+        sh->line0 = line;
+        sh->nlines = n;
+        line += n;
+        plan->shards.push_back(std::move(sh));
+    }
+    return plan;
+}
+
+template<class F>
+static void for_each_shard(I3B_Plan& plan, F f)
+{
+    if (plan.shards.size() == 1) {
+        f(*plan.shards[0]);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (auto& shp : plan.shards) {
+        Shard* sh = shp.get();
+        th.emplace_back([sh, &f]() {
+            try {
+                f(*sh);
+            } catch (const ApiError& e) {
+                sh->status_code = e.code;
+                sh->error = e.what();
+            } catch (const std::exception& e) {
+                sh->status_code = I3B_EXC_RUNTIME_ERROR;
+                sh->error = e.what();
+            }
+        });
+    }
+    for (auto& t : th) t.join();
+    for (auto& shp : plan.shards)
+        if (shp->status_code < 0) throw ApiError(shp->status_code, shp->error);
+}
+
+static int merge_status(I3B_Plan& plan)
+{
+    int code = 0;
+    for (auto& sh : plan.shards)
+        if (sh->status_code > 0) code = sh->status_code;
+    return code;
+}
+
+static void merge_stats(I3B_Plan& plan, double ms_total)
+{
+    I3B_Stats t;
+    std::memset(&t, 0, sizeof t);
+    t.pulse_first = INT_MAX;
+    t.pulse_last = INT_MIN;
+    t.used_fast_kernel = 1;
+    for (auto& shp : plan.shards) {
+        const I3B_Stats& s = shp->stats;
+        t.pixel_pulses += s.pixel_pulses;
+        t.ms_h2d = std::max(t.ms_h2d, s.ms_h2d);
+        t.ms_target_solve = std::max(t.ms_target_solve, s.ms_target_solve);
+        t.ms_accumulate = std::max(t.ms_accumulate, s.ms_accumulate);
+        t.ms_d2h = std::max(t.ms_d2h, s.ms_d2h);
+        t.accumulate_launches += s.accumulate_launches;
+        t.total_launches += s.total_launches;
+        t.used_fast_kernel &= s.used_fast_kernel;
+        t.taps = s.taps;
+        t.h2d_bytes += s.h2d_bytes;
+        t.d2h_bytes += s.d2h_bytes;
+        if (s.pulse_last > s.pulse_first) {
+            t.pulse_first = std::min(t.pulse_first, s.pulse_first);
+            t.pulse_last = std::max(t.pulse_last, s.pulse_last);
+        }
+    }
+    if (t.pulse_first == INT_MAX) t.pulse_first = t.pulse_last = 0;
+    t.ms_total = ms_total;
+    t.n_devices = (int) plan.shards.size();
+    g_last_stats = t;
+}
+
+template<class F>
+static int guarded(F&& f)
+{
+    try {
+        return f();
+    } catch (const ApiError& e) {
+        g_last_error = e.what();
+        return e.code;
+    } catch (const std::bad_alloc&) {
+        g_last_error = "out of host memory";
+        return I3B_EXC_RUNTIME_ERROR;
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        return I3B_EXC_RUNTIME_ERROR;
+    }
+}
+
+} // namespace i3b
+
+extern "C" {
+
+int i3b_backproject(const I3B_BackprojectArgs* args)
+{
+    return guarded([&]() {
+        const auto t0 = std::chrono::steady_clock::now();
+        if (args && !args->out) throw ApiError(I3B_EXC_INVALID_ARGUMENT, "output array is null");
+        auto plan = make_plan(args);
+        float* out = args->out;
+        float* height = args->height;
+        for_each_shard(*plan, [&](Shard& sh) {
+            shard_setup(plan->hs, sh);
+            // the one-shot call streams from the caller's buffer (no deep copy of `in`)
+            shard_solve(plan->hs, sh);
+            shard_run(plan->hs, sh, false);
+            shard_download(plan->hs, sh, out, height);
+        });
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        merge_stats(*plan, ms);
+        return merge_status(*plan);
+    });
+}
+
+int i3b_plan_create(const I3B_BackprojectArgs* args, I3B_Plan** out_plan)
+{
+    return guarded([&]() {
+        if (!out_plan) throw ApiError(I3B_EXC_INVALID_ARGUMENT, "null plan pointer");
+        *out_plan = nullptr;
+        auto plan = make_plan(args);
+        for_each_shard(*plan, [&](Shard& sh) {
+            shard_setup(plan->hs, sh);
+            shard_solve(plan->hs, sh);   // needed to know which pulses to keep resident
+            shard_run(plan->hs, sh, true); // upload only
+        });
+        plan->hs.a.in = nullptr; // the caller's buffer is no longer referenced
+        plan->hs.a.out = nullptr;
+        plan->hs.a.height = nullptr;
+        *out_plan = plan.release();
+        return 0;
+    });
+}
+
+int i3b_plan_execute(I3B_Plan* plan)
+{
+    return guarded([&]() {
+        if (!plan) throw ApiError(I3B_EXC_INVALID_ARGUMENT, "null plan");
+        const auto t0 = std::chrono::steady_clock::now();
+        for_each_shard(*plan, [&](Shard& sh) {
+            const int64_t h2d = sh.stats.h2d_bytes;
+            std::memset(&sh.stats, 0, sizeof sh.stats);
+            sh.stats.taps = sh.ap.kernel.taps;
+            sh.stats.h2d_bytes = h2d;
+            shard_solve(plan->hs, sh);
+            shard_run(plan->hs, sh, false);
+        });
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        merge_stats(*plan, ms);
+        return merge_status(*plan);
+    });
+}
+
+int i3b_plan_download(I3B_Plan* plan, float* out, float* height)
+{
+    return guarded([&]() {
+        if (!plan) throw ApiError(I3B_EXC_INVALID_ARGUMENT, "null plan");
+        for_each_shard(*plan, [&](Shard& sh) { shard_download(plan->hs, sh, out, height); });
+        return 0;
+    });
+}
+
+int i3b_plan_destroy(I3B_Plan* plan)
+{
+    return guarded([&]() {
+        delete plan;
+        return 0;
+    });
+}
+
+int i3b_last_stats(I3B_Stats* stats)
+{
+    if (!stats) return I3B_EXC_INVALID_ARGUMENT;
+    *stats = g_last_stats;
+    return 0;
+}
+
+const char* i3b_last_error(void) { return g_last_error.c_str(); }
+
+const char* i3b_version(void) { return "isce3_b200 0.1.0 (sm_100a)"; }
+
+int i3b_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int i3b_measure_peaks(int device, I3B_Peaks* peaks)
+{
+    return guarded([&]() {
+        if (!peaks) throw ApiError(I3B_EXC_INVALID_ARGUMENT, "null peaks pointer");
+        const int rc = measure_peaks(device, peaks);
+        if (rc != 0) CK((cudaError_t) rc);
+        return 0;
+    });
+}
+
+} // extern "C"

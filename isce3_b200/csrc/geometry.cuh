@@ -1,0 +1,497 @@
+// FP64 device geometry for the per-pixel target solve and the per-pulse table.
+// Behavioural references (what must be matched, not how):
+//   orbit        cxx/isce3/core/detail/InterpolateOrbit.icc:15-109,116-155,161-193
+//   ellipsoid    cxx/isce3/core/Ellipsoid.h:99-102,152-158,177-224
+//   Brent        cxx/isce3/math/RootFind1dBracket.icc:57-216
+//   rdr2geo      cxx/isce3/geometry/detail/Rdr2Geo.icc:175-242
+//   geo2rdr      cxx/isce3/geometry/detail/Geo2Rdr.icc:185-238
+//   LUT2d / DEM  cxx/isce3/core/LUT2d.cpp:127-160, geometry/DEMInterpolator.cpp:592-659,
+//                core/{Bilinear,Bicubic,Spline2d,NearestNeighbor}Interpolator.cpp
+//   tropo        cxx/isce3/focus/DryTroposphereModel.icc:10-29
+// Everything is POD + templates: no device-side new, no virtual dispatch (the
+// reference's device twins use both, cuda/geometry/gpuDEMInterpolator.cu:69-90).
+#pragma once
+#include <cfloat>
+#include <cmath>
+
+#include "common.cuh"
+
+namespace i3b {
+
+enum { BORDER_ERROR = 0, BORDER_EXTRAPOLATE = 1, BORDER_FILLNAN = 2 };
+
+__device__ inline D3 ld3(const double* __restrict__ p, int i)
+{
+    return {p[3 * i], p[3 * i + 1], p[3 * i + 2]};
+}
+
+__device__ inline D3 nan3()
+{
+    const double q = nan("");
+    return {q, q, q};
+}
+
+// ---- orbit -----------------------------------------------------------------
+
+__device__ inline int linspace_search(double first, double spacing, int size, double val)
+{
+    const double last = first + (size - 1) * spacing;
+    if (spacing >= 0) {
+        if (val < first) return 0;
+        if (val > last) return size;
+    } else {
+        if (val > first) return 0;
+        if (val < last) return size;
+    }
+    return (int) ((val - first) / spacing + 1);
+}
+
+// Cubic Hermite through 4 state vectors (positions and velocities).
+__device__ inline void orbit_hermite(const DevOrbit& o, double t, D3* pos, D3* vel)
+{
+    int idx = linspace_search(o.t0, o.dt, o.n, t) - 2;
+    idx = min(max(idx, 0), o.n - 4);
+    double tt[4], d[4], h[4], hdot[4], gsum[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        tt[i] = o.t0 + (idx + i) * o.dt;
+        d[i] = t - tt[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        double s = 0., hh = 1., hd = 0.;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (j == i) continue;
+            const double inv = 1. / (tt[i] - tt[j]);
+            s += inv;
+            hh *= d[j] / (tt[i] - tt[j]);
+            double prod = inv;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (k == i || k == j) continue;
+                prod *= d[k] / (tt[i] - tt[k]);
+            }
+            hd += prod;
+        }
+        gsum[i] = s;
+        h[i] = hh;
+        hdot[i] = hd;
+    }
+    D3 p = {0, 0, 0}, v = {0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const double f0 = 1. - 2. * gsum[i] * d[i];
+        const double f1 = d[i];
+        const double g1 = h[i] + 2. * hdot[i] * d[i];
+        const double g0 = 2. * (f0 * hdot[i] - gsum[i] * h[i]);
+        const D3 P = ld3(o.pos, idx + i), V = ld3(o.vel, idx + i);
+        p = p + (h[i] * h[i]) * (P * f0 + V * f1);
+        v = v + h[i] * (P * g0 + V * g1);
+    }
+    *pos = p;
+    *vel = v;
+}
+
+// Eighth-order Legendre (Lagrange on 9 equispaced vectors).
+__device__ inline void orbit_legendre(const DevOrbit& o, double t, D3* pos, D3* vel)
+{
+    int idx = linspace_search(o.t0, o.dt, o.n, t) - 5;
+    idx = min(max(idx, 0), o.n - 9);
+    const double ta = o.t0 + idx * o.dt, tb = o.t0 + (idx + 8) * o.dt;
+    const double trel = 8. * (t - ta) / (tb - ta);
+    double teller = 1.;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) teller *= trel - i;
+    if (teller == 0.) {
+        const int i = (int) trel;
+        *pos = ld3(o.pos, idx + i);
+        *vel = ld3(o.vel, idx + i);
+        return;
+    }
+    const double noemer[9] = {40320.0, -5040.0, 1440.0, -720.0, 576.0,
+                              -720.0,  1440.0,  -5040.0, 40320.0};
+    D3 p = {0, 0, 0}, v = {0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        const double coeff = (teller / noemer[i]) / (trel - i);
+        p = p + coeff * ld3(o.pos, idx + i);
+        v = v + coeff * ld3(o.vel, idx + i);
+    }
+    *pos = p;
+    *vel = v;
+}
+
+__device__ inline int orbit_interpolate(const DevOrbit& o, double t, int border, D3* pos, D3* vel)
+{
+    const int need = o.method == I3B_ORBIT_LEGENDRE ? 9 : 4;
+    if (o.n < need) return I3B_ORBIT_INTERP_SIZE_ERROR;
+    const double tstart = o.t0, tend = o.t0 + (o.n - 1) * o.dt;
+    if (t < tstart || t > tend) {
+        if (border == BORDER_FILLNAN) {
+            *pos = nan3();
+            *vel = nan3();
+        }
+        if (border != BORDER_EXTRAPOLATE) return I3B_ORBIT_INTERP_DOMAIN_ERROR;
+    }
+    if (o.method == I3B_ORBIT_HERMITE) {
+        orbit_hermite(o, t, pos, vel);
+        return I3B_SUCCESS;
+    }
+    if (o.method == I3B_ORBIT_LEGENDRE) {
+        orbit_legendre(o, t, pos, vel);
+        return I3B_SUCCESS;
+    }
+    return I3B_ORBIT_INTERP_UNKNOWN_METHOD;
+}
+
+// ---- WGS84 ellipsoid ------------------------------------------------------
+
+__device__ inline D3 llh_to_xyz(D3 llh)
+{
+    double slat, clat, slon, clon;
+    sincos(llh.y, &slat, &clat);
+    sincos(llh.x, &slon, &clon);
+    const double re = kA / sqrt(1.0 - kE2 * slat * slat);
+    return {(re + llh.z) * clat * clon, (re + llh.z) * clat * slon,
+            (re * (1.0 - kE2) + llh.z) * slat};
+}
+
+// Vermeille (2002) closed form.
+__device__ inline D3 xyz_to_llh(D3 p3)
+{
+    const double e4 = kE2 * kE2, a2 = kA * kA;
+    const double rho2 = p3.x * p3.x + p3.y * p3.y;
+    const double p = rho2 / a2;
+    const double q = (1. - kE2) * (p3.z * p3.z) / a2;
+    const double r = (p + q - e4) / 6.;
+    const double s = (e4 * p * q) / (4. * r * r * r);
+    const double t = cbrt(1. + s + sqrt(s * (2. + s)));
+    const double u = r * (1. + t + (1. / t));
+    const double rv = sqrt(u * u + e4 * q);
+    const double w = (kE2 * (u + rv - q)) / (2. * rv);
+    const double k = sqrt(u + rv + w * w) - w;
+    const double d = (k * sqrt(rho2)) / (k + kE2);
+    D3 llh;
+    llh.y = atan2(p3.z, d);
+    llh.x = atan2(p3.y, p3.x);
+    llh.z = ((k + kE2 - 1.) * sqrt(d * d + p3.z * p3.z)) / k;
+    return llh;
+}
+
+__device__ inline D3 n_vector(double lon, double lat)
+{
+    double slat, clat, slon, clon;
+    sincos(lat, &slat, &clat);
+    sincos(lon, &slon, &clon);
+    return {clat * clon, clat * slon, slat};
+}
+
+// ---- 2-D samplers -----------------------------------------------------------
+
+template<typename U>
+struct Grid2d {
+    const U* __restrict__ data;
+    int rows, cols;
+    __device__ U operator()(int r, int c) const { return data[(size_t) r * cols + c]; }
+};
+
+template<typename U>
+__device__ inline U bilinear(double x, double y, const Grid2d<U>& z)
+{
+    const int x1 = (int) floor(x), x2 = (int) ceil(x);
+    const int y1 = (int) floor(y), y2 = (int) ceil(y);
+    const U q11 = z(y1, x1), q12 = z(y2, x1), q21 = z(y1, x2), q22 = z(y2, x2);
+    if (y1 == y2 && x1 == x2) return q11;
+    if (y1 == y2) return U((x2 - x) / (x2 - x1)) * q11 + U((x - x1) / (x2 - x1)) * q21;
+    if (x1 == x2) return U((y2 - y) / (y2 - y1)) * q11 + U((y - y1) / (y2 - y1)) * q12;
+    const U den = U((x2 - x1) * (y2 - y1));
+    return (q11 * U((x2 - x) * (y2 - y))) / den + (q21 * U((x - x1) * (y2 - y))) / den +
+           (q12 * U((x2 - x) * (y - y1))) / den + (q22 * U((x - x1) * (y - y1))) / den;
+}
+
+template<typename U>
+__device__ inline U catmull_rom(U p0, U p1, U p2, U p3, double tf)
+{
+    const double tc = 1. - tf;
+    return (U(tf) * (p2 - p0 * U(tc * tc) + (p2 * U(tc * 3. + 1.) - p3 * U(tc)) * U(tf)) +
+            p1 * U(tf * tf * (tf * 3. - 5.) + 2.)) / U(2.);
+}
+
+template<typename U>
+__device__ inline U bicubic(double x, double y, const Grid2d<U>& z)
+{
+    const int x0 = (int) floor(x), y0 = (int) floor(y);
+    U rowv[4];
+#pragma unroll
+    for (int i = -1; i < 3; ++i)
+        rowv[i + 1] = catmull_rom<U>(z(y0 + i, x0 - 1), z(y0 + i, x0), z(y0 + i, x0 + 1),
+                                     z(y0 + i, x0 + 2), x - x0);
+    return catmull_rom<U>(rowv[0], rowv[1], rowv[2], rowv[3], y - y0);
+}
+
+// Natural cubic spline through N points, second derivatives by the usual
+// tridiagonal sweep; "biquintic" in the reference is this with N = 6.
+template<typename U, int N>
+__device__ inline void spline_init(const U* Y, U* R, U* Q)
+{
+    Q[0] = U(0);
+    R[0] = U(0);
+#pragma unroll
+    for (int i = 1; i < N - 1; ++i) {
+        const U p = U(1.0) / (U(0.5) * Q[i - 1] + U(2.0));
+        Q[i] = U(-0.5) * p;
+        R[i] = (U(3.0) * (Y[i + 1] - U(2.0) * Y[i] + Y[i - 1]) - U(0.5) * R[i - 1]) * p;
+    }
+    R[N - 1] = U(0);
+#pragma unroll
+    for (int i = N - 2; i > 0; --i) R[i] = Q[i] * R[i + 1] + R[i];
+}
+
+template<typename U, int N>
+__device__ inline U spline_eval(double x, const U* Y, const U* R)
+{
+    const U denom = U(6.0);
+    if (x < 1.0) return Y[0] + U(x - 1.0) * (Y[1] - Y[0] - (R[1] / denom));
+    if (x > N) return Y[N - 1] + U(x - N) * (Y[N - 1] - Y[N - 2] + (R[N - 2] / denom));
+    const int j = (int) floor(x);
+    const U xx = U(x - j);
+    // static unrolled select keeps Y/R in registers (no local-memory indexing)
+    U yj = Y[1], yjm = Y[0], rj = R[1], rjm = R[0];
+#pragma unroll
+    for (int q = 2; q < N; ++q)
+        if (j == q) {
+            yj = Y[q];
+            yjm = Y[q - 1];
+            rj = R[q];
+            rjm = R[q - 1];
+        }
+    if (j >= N) { // x == N exactly: reference indexes Y[N] (out of range); clamp
+        yj = Y[N - 1];
+        yjm = Y[N - 2];
+        rj = R[N - 1];
+        rjm = R[N - 2];
+    }
+    const U t0 = yj - yjm - (rjm / U(3.0)) - (rj / denom);
+    const U t1 = xx * ((rjm / U(2.0)) + (xx * ((rj - rjm) / denom)));
+    return yjm + (xx * (t0 + t1));
+}
+
+template<typename U>
+__device__ inline U biquintic(double x, double y, const Grid2d<U>& z)
+{
+    constexpr int N = 6;
+    int i0 = (int) y, j0 = (int) x;
+    i0 = i0 - (N / 2) + 1;
+    j0 = j0 - (N / 2) + 1;
+    U A[N], R[N], Q[N], HC[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const int indi = min(max(i0 + i, 0), z.rows - 2);
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            const int indj = min(max(j0 + j, 0), z.cols - 2);
+            A[j] = z(indi + 1, indj + 1);
+        }
+        spline_init<U, N>(A, R, Q);
+        HC[i] = spline_eval<U, N>(x - j0, A, R);
+    }
+    spline_init<U, N>(HC, R, Q);
+    return spline_eval<U, N>(y - i0, HC, R);
+}
+
+template<typename U>
+__device__ inline U interp2d(int method, double x, double y, const Grid2d<U>& z)
+{
+    switch (method) {
+    case I3B_INTERP_BICUBIC: return bicubic<U>(x, y, z);
+    case I3B_INTERP_BIQUINTIC: return biquintic<U>(x, y, z);
+    case I3B_INTERP_NEAREST: return z((int) round(y), (int) round(x));
+    default: return bilinear<U>(x, y, z);
+    }
+}
+
+__device__ inline double lut2d_eval(const DevLUT2d& l, double y, double x)
+{
+    if (!l.have_data) return l.ref_value;
+    double xi = (x - l.xstart) / l.dx;
+    double yi = (y - l.ystart) / l.dy;
+    xi = fmin(fmax(xi, 0.0), l.width - 1.0);
+    yi = fmin(fmax(yi, 0.0), l.length - 1.0);
+    const Grid2d<double> g {l.data, l.length, l.width};
+    return interp2d<double>(l.method, xi, yi, g);
+}
+
+__device__ inline double dem_interp_lonlat(const DevDEM& d, double lon, double lat)
+{
+    if (!d.have_raster) return d.ref_height;
+    double x = lon * 180.0 / M_PI; // LonLat::forward, core/Projections.h:127-133
+    const double y = lat * 180.0 / M_PI;
+    if (x > 360 || x < -360) x = fmod(x, 360.);
+    if (x < -180) x += 360;
+    if (x - 360 >= d.xstart) {
+        x -= 360;
+    } else if (x < d.xstart && x + 360 >= d.xstart) {
+        x += 360;
+    } else if (x < d.xstart) {
+        return d.ref_height;
+    }
+    const double row = (y - d.ystart) / d.dy;
+    const double col = (x - d.xstart) / d.dx;
+    const int irow = (int) floor(row), icol = (int) floor(col);
+    if (irow < 2 || irow >= d.length - 1) return d.ref_height;
+    if (icol < 2 || icol >= d.width - 1) return d.ref_height;
+    const Grid2d<float> g {d.data, d.length, d.width};
+    return interp2d<float>(d.method, col, row, g);
+}
+
+// ---- Brent's bracketing root finder ---------------------------------------------
+
+__device__ inline bool opposite_sign(double a, double b) { return signbit(a) != signbit(b); }
+
+template<class F>
+__device__ inline int brent(double a, double b, F f, const double tol, double* root)
+{
+    if (tol < 0.0) return I3B_INVALID_TOLERANCE;
+    double c, d, e, fa, fb, fc, p, q, r, s, tol1;
+    fa = f(a);
+    if (fa == 0.0) {
+        *root = a;
+        return I3B_SUCCESS;
+    }
+    fb = f(b);
+    if (fb == 0.0) {
+        *root = b;
+        return I3B_SUCCESS;
+    }
+    if (!opposite_sign(fa, fb)) return I3B_INVALID_INTERVAL;
+    c = a;
+    fc = fa;
+    e = d = b - a;
+    tol1 = tol > 0.0 ? tol : DBL_EPSILON;
+    const int maxiter = 3 * (int) ceil(log2(fabs((a - b) / tol1)));
+    for (int it = 0; it < maxiter; ++it) {
+        if (fabs(fc) < fabs(fb)) {
+            a = b; b = c; c = a;
+            fa = fb; fb = fc; fc = fa;
+        }
+        tol1 = 2 * DBL_EPSILON * fabs(b) + 0.5 * tol;
+        const double xm = 0.5 * (c - b);
+        if ((fabs(xm) <= tol1) || (fb == 0.0)) {
+            *root = b;
+            return I3B_SUCCESS;
+        }
+        if ((fabs(e) < tol1) || (fabs(fa) <= fabs(fb))) {
+            e = d = xm;
+        } else {
+            s = fb / fa;
+            if (a == c) {
+                p = 2 * xm * s;
+                q = 1.0 - s;
+            } else {
+                q = fa / fc;
+                r = fb / fc;
+                p = s * (2 * xm * q * (q - r) - (b - a) * (r - 1.0));
+                q = (q - 1.0) * (r - 1.0) * (s - 1.0);
+            }
+            if (p > 0.0) q = -q; else p = -p;
+            s = e;
+            e = d;
+            if (((2 * p) >= (3 * xm * q - fabs(tol1 * q))) || (p >= fabs(0.5 * s * q))) {
+                e = d = xm;
+            } else {
+                d = p / q;
+            }
+        }
+        a = b;
+        fa = fb;
+        if (fabs(d) <= tol1) b = (xm <= 0.0) ? b - tol1 : b + tol1;
+        else b = b + d;
+        fb = f(b);
+        if (!opposite_sign(fb, fc)) {
+            c = a;
+            fc = fa;
+            e = d = b - a;
+        }
+    }
+    *root = b;
+    return I3B_FAILED_TO_CONVERGE;
+}
+
+// ---- rdr2geo / geo2rdr (bracketing solvers) -----------------------------------------
+
+// Target ECEF on the DEM for (aztime, range, doppler).  Returns I3B_SUCCESS, a soft
+// ErrorCode, or I3B_EXC_OUT_OF_RANGE when aztime is outside the orbit (the CPU
+// reference throws there, core/Orbit.cpp:78-83).
+__device__ inline int rdr2geo_bracket(double aztime, double slant_range, double doppler,
+                                      const DevOrbit& orbit, const DevDEM& dem, double wavelength,
+                                      int side, const I3B_Rdr2GeoBracketParams& prm, D3* xyz)
+{
+    D3 radar, velocity;
+    if (orbit_interpolate(orbit, aztime, BORDER_ERROR, &radar, &velocity) != I3B_SUCCESS)
+        return I3B_EXC_OUT_OF_RANGE;
+    const double speed = norm(velocity);
+    const D3 along = velocity / speed;
+    const D3 right = unit(cross(along, radar));
+    const D3 down = cross(along, right);
+    const D3 horizontal = (side == I3B_LOOK_RIGHT) ? right : -1.0 * right;
+    const double sin_squint = doppler * wavelength / (2 * speed);
+    const double cos_squint = sqrt(1.0 - sin_squint * sin_squint);
+    const D3 center = radar + (sin_squint * slant_range) * along;
+    const double radius = cos_squint * slant_range;
+    auto get_xyz = [&](double look) {
+        double sl, cl;
+        sincos(look, &sl, &cl);
+        return center + (radius * sl) * horizontal + (radius * cl) * down;
+    };
+    auto dh = [&](double look) {
+        const D3 llh = xyz_to_llh(get_xyz(look));
+        return llh.z - dem_interp_lonlat(dem, llh.x, llh.y);
+    };
+    const double tol_look = prm.tol_height / radius;
+    double look = 0.0;
+    const int err = brent(prm.look_min, prm.look_max, dh, tol_look, &look);
+    if (err != I3B_SUCCESS) return err;
+    *xyz = get_xyz(look);
+    return I3B_SUCCESS;
+}
+
+__device__ inline int geo2rdr_bracket(D3 x, const DevOrbit& orbit, const DevLUT2d& dop,
+                                      double wavelength, int side,
+                                      const I3B_Geo2RdrBracketParams& prm, double* aztime,
+                                      double* range)
+{
+    const double orbit_start = orbit.t0, orbit_end = orbit.t0 + (orbit.n - 1) * orbit.dt;
+    double t0, t1;
+    if (prm.has_time_start) t0 = prm.time_start;
+    else t0 = dop.have_data ? fmax(orbit_start, dop.ystart) : orbit_start;
+    if (prm.has_time_end) t1 = prm.time_end;
+    else t1 = dop.have_data ? fmin(orbit_end, dop.ystart + dop.dy * (dop.length - 1)) : orbit_end;
+    D3 xp, v, r;
+    auto doppler_error = [&](double t) {
+        orbit_interpolate(orbit, t, BORDER_FILLNAN, &xp, &v);
+        r = x - xp;
+        const double rnorm = norm(r);
+        const double fd = lut2d_eval(dop, t, rnorm);
+        return 2.0 / wavelength * dot(v, r) / rnorm - fd;
+    };
+    const int err = brent(t0, t1, doppler_error, prm.tol_aztime, aztime);
+    if (err != I3B_SUCCESS) return err;
+    orbit_interpolate(orbit, *aztime, BORDER_FILLNAN, &xp, &v);
+    r = x - xp;
+    *range = norm(r);
+    const bool positive = dot(cross(r, v), xp) > 0;
+    if ((side == I3B_LOOK_RIGHT) ^ positive) return I3B_WRONG_LOOK_SIDE;
+    return I3B_SUCCESS;
+}
+
+__device__ inline double dry_tropo_tsx(D3 p, D3 llh)
+{
+    constexpr double ZPD = 2.3, H = 6000.;
+    const D3 x = llh_to_xyz(llh);
+    const D3 r_hat = unit(p - x);
+    const D3 n_hat = unit(n_vector(llh.x, llh.y));
+    return 2. * ZPD * exp(-llh.z / H) / (kC * dot(r_hat, n_hat));
+}
+
+} // namespace i3b

@@ -1,0 +1,215 @@
+// Per-pulse table, per-pixel target solve, generic accumulation and finalisation
+// kernels of the B200 TDBP backend (sm_100a).  All geometry here is FP64 and is
+// O(pulses) or O(pixels); the O(pixels x pulses) product kernel is accumulate_fast.cu.
+#include "geometry.cuh"
+#include "kernels.cuh"
+#include "launch.h"
+
+#include <climits>
+
+namespace i3b {
+
+// ---- per-pulse table ---------------------------------------------------------
+// Replaces the host loop Backproject.cpp:101-106 (orbit border mode Error).
+__global__ void pulse_table_kernel(DevOrbit orbit, Linspace in_time, double fc, PulseRec* pulse,
+                                   double* pv, DevStatus* status)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= in_time.size) return;
+    D3 p, v;
+    const int st = orbit_interpolate(orbit, in_time[k], BORDER_ERROR, &p, &v);
+    if (st != I3B_SUCCESS) {
+        status->hard_error = I3B_EXC_OUT_OF_RANGE;
+        p = v = nan3();
+    }
+    pv[6 * k + 0] = p.x; pv[6 * k + 1] = p.y; pv[6 * k + 2] = p.z;
+    pv[6 * k + 3] = v.x; pv[6 * k + 4] = v.y; pv[6 * k + 5] = v.z;
+    const double A = 2.0 / (dot(v, v) - kC * kC);
+    PulseRec r;
+    r.m2px = -2.0 * p.x; r.m2py = -2.0 * p.y; r.m2pz = -2.0 * p.z;
+    r.pp = dot(p, p);
+    const double fA = fc * A;
+    r.vBx = fA * v.x; r.vBy = fA * v.y; r.vBz = fA * v.z;
+    r.E = -fA * dot(p, v);
+    r.Cs = -fA * kC;
+    r.pad = 0.0;
+    pulse[k] = r;
+}
+
+// ---- per-pixel target solve -------------------------------------------------------
+// One thread per output pixel: Backproject.cpp:128-199 (rdr2geo_bracket on the output
+// geometry, LLH, geo2rdr_bracket on the input geometry, CPI bounds, dry-troposphere
+// delay) fused into one kernel that writes a 40-byte record per pixel instead of the
+// reference CUDA path's ~136 B of FP64 side tables (cuda/focus/Backproject.cu:526-640).
+__global__ void __launch_bounds__(128)
+target_solve_kernel(SolveParams P, PixelRec* __restrict__ pix, float* __restrict__ height,
+                    DevStatus* status)
+{
+    const long long tid = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    const long long npix = (long long) P.out_lines * P.out_width;
+    int kstart = -1, kstop = -1;
+    if (tid < npix) {
+        const int j = (int) (tid / P.out_width) + P.line0;
+        const int i = (int) (tid % P.out_width);
+        const double t = P.out_time[j];
+        const double r = P.out_range[i];
+        const double fD = lut2d_eval(P.out_doppler, t, r);
+        PixelRec rec;
+        rec.x = rec.y = rec.z = nan("");
+        rec.tau_atm = 0.0;
+        float h = nanf("");
+        D3 x;
+        int st = rdr2geo_bracket(t, r, fD, P.out_orbit, P.dem, P.wvl, P.out_side, P.r2g, &x);
+        if (st == I3B_EXC_OUT_OF_RANGE) {
+            status->hard_error = st;
+        } else if (st != I3B_SUCCESS) {
+            status->soft_error = I3B_FAILED_TO_CONVERGE;
+        } else {
+            const D3 llh = xyz_to_llh(x);
+            h = (float) llh.z;
+            double tc, rc;
+            st = geo2rdr_bracket(x, P.in_orbit, P.in_doppler, P.wvl, P.in_side, P.g2r, &tc, &rc);
+            if (st != I3B_SUCCESS) {
+                status->soft_error = I3B_FAILED_TO_CONVERGE;
+            } else {
+                D3 p, v;
+                orbit_interpolate(P.in_orbit, tc, BORDER_FILLNAN, &p, &v);
+                const double l = P.wvl * rc * (norm(p) / norm(x)) / (2. * P.ds);
+                const double cpi = l / norm(v);
+                const double tstart = tc - 0.5 * cpi, tstop = tc + 0.5 * cpi;
+                const double t0 = P.in_time.first, dt = P.in_time.spacing;
+                kstart = (int) floor((tstart - t0) / dt);
+                kstop = (int) ceil((tstop - t0) / dt);
+                kstart = max(kstart, 0);
+                kstop = min(kstop, P.in_time.size);
+                double tau_atm = 0.;
+                if (P.tropo == I3B_TROPO_TSX) tau_atm = dry_tropo_tsx(p, llh);
+                rec.x = x.x; rec.y = x.y; rec.z = x.z;
+                rec.tau_atm = tau_atm;
+                if (kstop < kstart) kstop = kstart; // empty window -> zero pixel (CPU loop runs 0 times)
+            }
+        }
+        rec.kstart = kstart;
+        rec.kstop = kstop;
+        pix[tid] = rec;
+        if (height) height[tid] = h;
+    }
+    // block-level reduction of the pulse span and the work count
+    int kmin = (kstart >= 0 && kstop > kstart) ? kstart : INT_MAX;
+    int kmax = (kstart >= 0 && kstop > kstart) ? kstop : INT_MIN;
+    unsigned long long pp = (kstart >= 0) ? (unsigned long long) (kstop - kstart) : 0ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+        kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+        pp += __shfl_xor_sync(0xffffffffu, pp, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (kmin != INT_MAX) atomicMin(&status->kmin, kmin);
+        if (kmax != INT_MIN) atomicMax(&status->kmax, kmax);
+        if (pp) atomicAdd(&status->pixel_pulses, pp);
+    }
+}
+
+// ---- generic accumulation (exact kernel evaluation, FP64 throughout) ---------------
+// sumCoherent, Backproject.cpp:30-63, with the CPU path's zero-padded edge windows
+// (core/detail/Interp1d.h:54-80).  Used for kernels the fast path cannot represent
+// (Bartlett/Linear kinks, unsupported tap counts) and as an on-device cross-check.
+__global__ void __launch_bounds__(256)
+accumulate_generic_kernel(AccumParams P, const PixelRec* __restrict__ pix,
+                          const double* __restrict__ pv, const float2* __restrict__ rc,
+                          double2* __restrict__ acc)
+{
+    const long long tid = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= P.npix) return;
+    if (P.tile_mask) {
+        const int j = (int) (tid / P.out_width), i = (int) (tid % P.out_width);
+        if (!P.tile_mask[(j / P.tile_az) * P.tiles_rg + (i / P.tile_rg)]) return;
+    }
+    const PixelRec rec = pix[tid];
+    if (rec.kstart < 0) return;
+    const int k0 = max(rec.kstart, P.k_begin), k1 = min(rec.kstop, P.k_end);
+    if (k1 <= k0) return;
+    const D3 x = {rec.x, rec.y, rec.z};
+    const double tau_atm = rec.tau_atm;
+    const int W = P.kernel.taps;
+    double sr = 0., si = 0.;
+    for (int k = k0; k < k1; ++k) {
+        const D3 p = {pv[6 * k], pv[6 * k + 1], pv[6 * k + 2]};
+        const D3 v = {pv[6 * k + 3], pv[6 * k + 4], pv[6 * k + 5]};
+        const D3 rr = x - p;
+        const double tau = tau_atm + 2. * (dot(rr, v) - kC * norm(rr)) / (dot(v, v) - (kC * kC));
+        const double u = (tau - P.swst) / P.dtau;
+        const long long i0 = (W % 2 == 0) ? (long long) ceil(u) : (long long) round(u);
+        const long long low = i0 - W / 2;
+        const float2* line = rc + (size_t) (k - P.rc_k0) * P.rc_pitch;
+        float ar = 0.f, ai = 0.f;
+        for (int m = 0; m < W; ++m) {
+            const long long jj = low + m;
+            const float w = kernel_eval(P.kernel, (double) jj - u);
+            if (jj >= 0 && jj < P.nr) {
+                const float2 d = line[jj];
+                ar += w * d.x;
+                ai += w * d.y;
+            }
+        }
+        double sphi, cphi;
+        sincospi(2. * P.fc * tau, &sphi, &cphi);
+        sr += (double) ar * cphi - (double) ai * sphi;
+        si += (double) ar * sphi + (double) ai * cphi;
+    }
+    double2 a = acc[tid];
+    a.x += sr;
+    a.y += si;
+    acc[tid] = a;
+}
+
+// ---- finalisation: complex<double> accumulator -> complex64, NaN for failed pixels ---
+__global__ void finalize_kernel(long long npix, const PixelRec* __restrict__ pix,
+                                const double2* __restrict__ acc, float2* __restrict__ out)
+{
+    const long long tid = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= npix) return;
+    float2 o;
+    if (pix[tid].kstart < 0) {
+        o.x = o.y = nanf("");
+    } else {
+        const double2 a = acc[tid];
+        o.x = (float) a.x;
+        o.y = (float) a.y;
+    }
+    out[tid] = o;
+}
+
+// ---- launchers -------------------------------------------------------------------------
+
+void launch_pulse_table(const DevOrbit& orbit, Linspace in_time, double fc, PulseRec* pulse,
+                        double* pv, DevStatus* status, cudaStream_t s)
+{
+    const int n = in_time.size;
+    pulse_table_kernel<<<(n + 127) / 128, 128, 0, s>>>(orbit, in_time, fc, pulse, pv, status);
+}
+
+void launch_target_solve(const SolveParams& P, PixelRec* pix, float* height, DevStatus* status,
+                         cudaStream_t s)
+{
+    const long long npix = (long long) P.out_lines * P.out_width;
+    const unsigned grid = (unsigned) ((npix + 127) / 128);
+    target_solve_kernel<<<grid, 128, 0, s>>>(P, pix, height, status);
+}
+
+void launch_accumulate_generic(const AccumParams& P, const PixelRec* pix, const double* pv,
+                               const float2* rc, double2* acc, cudaStream_t s)
+{
+    const unsigned grid = (unsigned) ((P.npix + 255) / 256);
+    accumulate_generic_kernel<<<grid, 256, 0, s>>>(P, pix, pv, rc, acc);
+}
+
+void launch_finalize(long long npix, const PixelRec* pix, const double2* acc, float2* out,
+                     cudaStream_t s)
+{
+    const unsigned grid = (unsigned) ((npix + 255) / 256);
+    finalize_kernel<<<grid, 256, 0, s>>>(npix, pix, acc, out);
+}
+
+} // namespace i3b
