@@ -176,11 +176,11 @@ class BackprojectPlan:
 
     def __init__(self, out_geometry, in_, in_geometry, dem, fc, ds, kernel,
                  dry_tropo_model="tsx", rdr2geo_params=None, geo2rdr_params=None, batch=1024,
-                 force_generic=False):
+                 force_generic=False, devices=None):
         self._lib = _capi.load_library()
         self._shape = (out_geometry.grid_length, out_geometry.grid_width)
         fl = build_args(None, out_geometry, in_, in_geometry, dem, fc, ds, kernel,
-                        dry_tropo_model, rdr2geo_params, geo2rdr_params, batch, None, None,
+                        dry_tropo_model, rdr2geo_params, geo2rdr_params, batch, None, devices,
                         force_generic)
         self._handle = C.c_void_p()
         status = self._lib.i3b_plan_create(C.byref(fl.args), C.byref(self._handle))
