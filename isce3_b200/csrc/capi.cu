@@ -456,9 +456,11 @@ static void shard_run(const HostScene& hs, Shard& sh, bool resident_only)
         sh.stats.ms_h2d = ms_h2d;
         return;
     }
-    launch_finalize(sh.ap.npix, sh.pix.p, sh.acc.p, sh.out.p, s);
-    CK(cudaGetLastError());
-    sh.stats.total_launches += 1;
+    if (sh.ap.npix > 0) {
+        launch_finalize(sh.ap.npix, sh.pix.p, sh.acc.p, sh.out.p, s);
+        CK(cudaGetLastError());
+        sh.stats.total_launches += 1;
+    }
     DevStatus st;
     CK(cudaMemcpyAsync(&st, sh.status.p, sizeof st, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));

@@ -288,6 +288,8 @@ def _dem_sample_fn(dem: DEMInterpolator):
         col = (math.degrees(lon) - dem.x_start) / dem.delta_x
         row = (math.degrees(lat) - dem.y_start) / dem.delta_y
         c0, r0 = int(math.floor(col)), int(math.floor(row))
+        if r0 < 2 or r0 >= dem.length - 1 or c0 < 2 or c0 >= dem.width - 1:
+            return dem.ref_height  # same margin rule as DEMInterpolator.cpp:649-653
         fc_, fr = col - c0, row - r0
         z = dem.data
         return float(z[r0, c0] * (1 - fc_) * (1 - fr) + z[r0, c0 + 1] * fc_ * (1 - fr) +
