@@ -26,6 +26,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -50,8 +51,12 @@ constexpr int MAX_COEF = 8;   // degree <= 7
 // Polynomial coefficients of the per-tap weights, in f = frac - 0.5 in [-0.5, 0.5):
 //   w_m(f) = E_m(f^2) + f * O_m(f^2),  w_{K-1-m}(f) = E_m(f^2) - f * O_m(f^2)
 // c_even[m][i] multiplies f^(2i), c_odd[m][i] multiplies f^(2i+1); m < ceil(K/2).
-__constant__ float c_even[MAX_TAPS / 2 + 1][MAX_COEF / 2];
-__constant__ float c_odd[MAX_TAPS / 2 + 1][MAX_COEF / 2];
+// One 32-byte row per tap pair {e0..e3, o0..o3} so a row is two 128-bit constant loads.
+struct __align__(16) TapPoly {
+    float e[MAX_COEF / 2];
+    float o[MAX_COEF / 2];
+};
+__constant__ TapPoly c_poly[MAX_TAPS / 2 + 1];
 
 // ---- PTX wrappers --------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p)
@@ -152,30 +157,85 @@ __device__ inline double sample_coord(const double* c, const PulseRec& r, double
     return fma(tcyc, G, -U0);
 }
 
+// ---- packed FP32x2 arithmetic (Blackwell FFMA2: one issue slot, two FMAs) -----------------
+// A 64-bit register pair holds (lo, hi).  ptxas folds pack2(x, x) into the scalar-broadcast
+// operand form of FFMA2 (R.F32), so "real weight x complex sample" is ONE instruction.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi)
+{
+    f32x2 d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+    return d;
+}
+__device__ __forceinline__ f32x2 bcast2(float x) { return pack2(x, x); }
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
+{
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b)
+{
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ f32x2 lds64(uint32_t addr)
+{
+    f32x2 v;
+    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ double2 lds_d2(uint32_t addr)
+{
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+
 template<int K, int D>
 struct Weights {
-    // evaluates the K tap weights for fractional offset f (in [-0.5, 0.5))
-    __device__ static __forceinline__ void eval(float f, float (&w)[K])
+    // Tap weights of TWO pixels at once: f = (f_pixel0, f_pixel1) in [-0.5, 0.5);
+    // w[m] = (w_m(f0), w_m(f1)).  Coefficients enter as scalar-broadcast operands.
+    __device__ static __forceinline__ void eval(f32x2 f, f32x2 (&w)[K])
     {
         constexpr int NE = D / 2 + 1;       // even coefficients  f^0, f^2, ...
         constexpr int NO = (D + 1) / 2;     // odd coefficients   f^1, f^3, ...
-        const float h = f * f;
+        const f32x2 h = mul2(f, f);
+        const f32x2 nf = mul2(f, bcast2(-1.0f));
 #pragma unroll
         for (int m = 0; m < K / 2; ++m) {
-            float e = c_even[m][NE - 1];
+            const float4 ce = *reinterpret_cast<const float4*>(c_poly[m].e);
+            const float4 co = *reinterpret_cast<const float4*>(c_poly[m].o);
+            const float cev[4] = {ce.x, ce.y, ce.z, ce.w}, cov[4] = {co.x, co.y, co.z, co.w};
+            f32x2 e = bcast2(cev[NE - 1]);
 #pragma unroll
-            for (int i = NE - 2; i >= 0; --i) e = fmaf(e, h, c_even[m][i]);
-            float o = c_odd[m][NO - 1];
+            for (int i = NE - 2; i >= 0; --i) e = fma2(e, h, bcast2(cev[i]));
+            f32x2 o = bcast2(cov[NO - 1]);
 #pragma unroll
-            for (int i = NO - 2; i >= 0; --i) o = fmaf(o, h, c_odd[m][i]);
-            w[m] = fmaf(f, o, e);
-            w[K - 1 - m] = fmaf(-f, o, e);
+            for (int i = NO - 2; i >= 0; --i) o = fma2(o, h, bcast2(cov[i]));
+            w[m] = fma2(f, o, e);
+            w[K - 1 - m] = fma2(nf, o, e);
         }
         if (K & 1) {
             constexpr int m = K / 2;
-            float e = c_even[m][NE - 1];
+            const float4 ce = *reinterpret_cast<const float4*>(c_poly[m].e);
+            const float cev[4] = {ce.x, ce.y, ce.z, ce.w};
+            f32x2 e = bcast2(cev[NE - 1]);
 #pragma unroll
-            for (int i = NE - 2; i >= 0; --i) e = fmaf(e, h, c_even[m][i]);
+            for (int i = NE - 2; i >= 0; --i) e = fma2(e, h, bcast2(cev[i]));
             w[m] = e;
         }
     }
@@ -187,11 +247,11 @@ struct PixState {
     double s1, s2, yh;    // range at the two previous pulses; 0.5 / range
     double upix;          // fc*tau_atm*G - U0 + shift
     double mphase;        // MAGIC + fc*tau_atm
-    float accr, acci;     // FP32 partial sums of the current pulse tile
-    int kstart, kstop;
+    f32x2 accp, accq;     // FP32 partial sums of the pulse tile: sum cos*(ar,ai), sum sin*(ar,ai)
+    int kstart, kspan;    // aperture: kstart <= k < kstart + kspan
 };
 
-template<int K, int D>
+template<int K, int D, int UNROLL>
 __global__ void __launch_bounds__(NTHREADS, 2)
 accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, FastParams P,
                        const PixelRec* __restrict__ pix, const PulseRec* __restrict__ pulse,
@@ -246,12 +306,14 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, FastParams P,
             const double t0cyc = P.fc * r.tau_atm;
             st[p].upix = fma(t0cyc, P.G, SHIFT - P.U0);
             st[p].mphase = MAGIC + t0cyc;
-            st[p].kstart = in_grid[p] ? max(r.kstart, P.k_begin) : 0;
-            st[p].kstop = in_grid[p] ? min(r.kstop, P.k_end) : 0;
-            st[p].accr = st[p].acci = 0.f;
-            if (st[p].kstop > st[p].kstart) {
-                kmin = min(kmin, st[p].kstart);
-                kmax = max(kmax, st[p].kstop);
+            const int ks = in_grid[p] ? max(r.kstart, P.k_begin) : 0;
+            const int ke_p = in_grid[p] ? min(r.kstop, P.k_end) : 0;
+            st[p].kstart = ks;
+            st[p].kspan = max(ke_p - ks, 0);
+            st[p].accp = st[p].accq = 0ull;
+            if (ke_p > ks) {
+                kmin = min(kmin, ks);
+                kmax = max(kmax, ke_p);
             }
             // the four corner pixels of the (grid-clipped) tile publish their position
             const int lc = lcol + p;
@@ -345,44 +407,48 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, FastParams P,
     double* accd = reinterpret_cast<double*>(smem_raw + HEADER_BYTES + NSTAGE * sbytes) + tid * (2 * PX);
 #pragma unroll
     for (int i = 0; i < 2 * PX; ++i) accd[i] = 0.0;
-    int overflow = 0;
+    unsigned jjmax = 0; // sticky maximum of the (unsigned) window offsets: overflow detector
     const float TWO_PI = 6.28318530717958647692f, THREE_PI = 9.42477796076937971538f;
+    const uint32_t stage_addr0 = smem_u32(stage0);
+    const uint32_t row_bytes = (uint32_t) P.W * (uint32_t) sizeof(float2);
+    const unsigned jmax = (unsigned) (P.W - (K + 3));
 
     for (int n = 0; n < ntiles; ++n) {
         if (warp == 0 && n + NSTAGE - 1 < ntiles) produce(n + NSTAGE - 1);
         const int s = n % NSTAGE;
         mbar_wait(&hdr->full[s], (n / NSTAGE) & 1);
-        const unsigned char* sp = stage0 + (size_t) s * sbytes;
-        const float2* lines = reinterpret_cast<const float2*>(sp);
-        const PulseRec* prec = reinterpret_cast<const PulseRec*>(sp + (size_t) TK * P.W * sizeof(float2));
+        const uint32_t lines_addr = stage_addr0 + (uint32_t) s * (uint32_t) sbytes;
+        const uint32_t prec_addr = lines_addr + (uint32_t) TK * row_bytes;
         // index constant: j0 = (mantissa >> 23) - CONST  (see MAGIC)
         const unsigned jconst = 0x80000000u + 0x10000000u + (unsigned) hdr->winlo[s] - (unsigned) LOWOFF;
-        const int kfirst = kb + n * TK;
-        const unsigned jmax = (unsigned) (P.W - (K + 3));
+        // k - kstart for the first pulse of the tile, per pixel
+        unsigned krel0 = (unsigned) (kb + n * TK - st[0].kstart);
+        unsigned krel1 = (unsigned) (kb + n * TK - st[1].kstart);
 
-#pragma unroll 1
+#pragma unroll UNROLL
         for (int kk = 0; kk < TK; ++kk) {
-            const PulseRec pr = prec[kk];
-            const int k = kfirst + kk;
+            const uint32_t pa = prec_addr + (uint32_t) kk * (uint32_t) sizeof(PulseRec);
+            const double2 c0 = lds_d2(pa), c1 = lds_d2(pa + 16), c2 = lds_d2(pa + 32),
+                          c3 = lds_d2(pa + 48), c4 = lds_d2(pa + 64);
+            // PulseRec: m2px m2py | m2pz pp | vBx vBy | vBz E | Cs pad
             float f[PX], cs[PX], sn[PX];
             unsigned j0[PX];
-            bool clamped[PX];
 #pragma unroll
             for (int p = 0; p < PX; ++p) {
                 PixState& q = st[p];
-                const double r2 = fma(q.x, pr.m2px, fma(q.y, pr.m2py, fma(q.z, pr.m2pz, q.xx + pr.pp)));
+                const double r2 = fma(q.x, c0.x, fma(q.y, c0.y, fma(q.z, c1.x, q.xx + c1.y)));
                 const double spred = fma(2.0, q.s1, -q.s2);
                 const double e = fma(-spred, spred, r2);
                 const double sv = fma(e, q.yh, spred);
                 q.s2 = q.s1;
                 q.s1 = sv;
-                const double tgeo = fma(pr.Cs, sv, fma(q.x, pr.vBx, fma(q.y, pr.vBy, fma(q.z, pr.vBz, pr.E))));
+                const double tgeo = fma(c4.x, sv, fma(q.x, c2.x, fma(q.y, c2.y, fma(q.z, c3.x, c3.y))));
                 const double mu = fma(tgeo, P.G, q.upix) + MAGIC;
                 const double mt = tgeo + q.mphase;
                 const unsigned ulo = (unsigned) __double2loint(mu), uhi = (unsigned) __double2hiint(mu);
                 f[p] = __uint_as_float((ulo & 0x007FFFFFu) | 0x3F800000u) - 1.5f;
                 const unsigned jj = __funnelshift_r(ulo, uhi, 23) - jconst;
-                clamped[p] = jj > jmax;
+                jjmax = max(jjmax, jj);
                 j0[p] = min(jj, jmax);
                 const unsigned tlo = (unsigned) __double2loint(mt);
                 const float v = __uint_as_float((tlo & 0x007FFFFFu) | 0x3F800000u);
@@ -391,65 +457,68 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, FastParams P,
                 cs[p] = __cosf(ang);
                 sn[p] = __sinf(ang);
             }
-            const float2* line = lines + (size_t) kk * P.W;
+            const uint32_t line_addr = lines_addr + (uint32_t) kk * row_bytes;
+            f32x2 w[K];
+            Weights<K, D>::eval(pack2(f[0], f[1]), w);
             float w0[K], w1[K];
-            Weights<K, D>::eval(f[0], w0);
-            Weights<K, D>::eval(f[1], w1);
-            float ar0 = 0.f, ai0 = 0.f, ar1 = 0.f, ai1 = 0.f;
+#pragma unroll
+            for (int m = 0; m < K; ++m) unpack2(w[m], w0[m], w1[m]);
+            f32x2 a0 = 0ull, a1 = 0ull; // (re, im) of the interpolated sample, pixel 0 / 1
             if (j0[1] == j0[0] + 1) {
                 // shared register window: K+1 samples (+1 when the start is odd)
                 const unsigned base = j0[0] & ~1u;
-                constexpr int NV = (K + 3) / 2; // float4 loads covering K+2 samples
-                float4 v4[NV];
-                const float4* src = reinterpret_cast<const float4*>(line + base);
+                constexpr int NV = (K + 3) / 2; // 16-byte loads covering K+2 samples
+                f32x2 sm[2 * NV];
+                const uint32_t src = line_addr + base * (uint32_t) sizeof(float2);
 #pragma unroll
-                for (int i = 0; i < NV; ++i) v4[i] = src[i];
-                const float2* sm = reinterpret_cast<const float2*>(v4);
+                for (int i = 0; i < NV; ++i) {
+                    const float4 v4 = lds128(src + 16u * i);
+                    sm[2 * i] = pack2(v4.x, v4.y);
+                    sm[2 * i + 1] = pack2(v4.z, v4.w);
+                }
                 if (j0[0] & 1u) {
 #pragma unroll
                     for (int m = 0; m < K; ++m) {
-                        ar0 = fmaf(w0[m], sm[m + 1].x, ar0);
-                        ai0 = fmaf(w0[m], sm[m + 1].y, ai0);
-                        ar1 = fmaf(w1[m], sm[m + 2].x, ar1);
-                        ai1 = fmaf(w1[m], sm[m + 2].y, ai1);
+                        a0 = fma2(bcast2(w0[m]), sm[m + 1], a0);
+                        a1 = fma2(bcast2(w1[m]), sm[m + 2], a1);
                     }
                 } else {
 #pragma unroll
                     for (int m = 0; m < K; ++m) {
-                        ar0 = fmaf(w0[m], sm[m].x, ar0);
-                        ai0 = fmaf(w0[m], sm[m].y, ai0);
-                        ar1 = fmaf(w1[m], sm[m + 1].x, ar1);
-                        ai1 = fmaf(w1[m], sm[m + 1].y, ai1);
+                        a0 = fma2(bcast2(w0[m]), sm[m], a0);
+                        a1 = fma2(bcast2(w1[m]), sm[m + 1], a1);
                     }
                 }
             } else {
                 // general spacing: independent windows
+                const uint32_t s0 = line_addr + j0[0] * (uint32_t) sizeof(float2);
+                const uint32_t s1 = line_addr + j0[1] * (uint32_t) sizeof(float2);
 #pragma unroll
                 for (int m = 0; m < K; ++m) {
-                    const float2 a = line[j0[0] + m], b = line[j0[1] + m];
-                    ar0 = fmaf(w0[m], a.x, ar0);
-                    ai0 = fmaf(w0[m], a.y, ai0);
-                    ar1 = fmaf(w1[m], b.x, ar1);
-                    ai1 = fmaf(w1[m], b.y, ai1);
+                    a0 = fma2(bcast2(w0[m]), lds64(s0 + 8u * m), a0);
+                    a1 = fma2(bcast2(w1[m]), lds64(s1 + 8u * m), a1);
                 }
             }
-            if (k >= st[0].kstart && k < st[0].kstop) {
-                st[0].accr = fmaf(ar0, cs[0], fmaf(-ai0, sn[0], st[0].accr));
-                st[0].acci = fmaf(ar0, sn[0], fmaf(ai0, cs[0], st[0].acci));
-                if (clamped[0]) overflow = 1;
+            // rotate by the carrier phase and accumulate, only inside the pixel's aperture
+            if (krel0 + kk < (unsigned) st[0].kspan) {
+                st[0].accp = fma2(bcast2(cs[0]), a0, st[0].accp);
+                st[0].accq = fma2(bcast2(sn[0]), a0, st[0].accq);
             }
-            if (k >= st[1].kstart && k < st[1].kstop) {
-                st[1].accr = fmaf(ar1, cs[1], fmaf(-ai1, sn[1], st[1].accr));
-                st[1].acci = fmaf(ar1, sn[1], fmaf(ai1, cs[1], st[1].acci));
-                if (clamped[1]) overflow = 1;
+            if (krel1 + kk < (unsigned) st[1].kspan) {
+                st[1].accp = fma2(bcast2(cs[1]), a1, st[1].accp);
+                st[1].accq = fma2(bcast2(sn[1]), a1, st[1].accq);
             }
         }
-        // pulse tile done: fold FP32 partials into FP64, release the stage
+        // pulse tile done: fold FP32 partials into FP64, release the stage.
+        // sum s*e^{j phi} = (P.x - Q.y) + j (P.y + Q.x), negated (half-cycle shift above)
 #pragma unroll
         for (int p = 0; p < PX; ++p) {
-            accd[2 * p] -= (double) st[p].accr; // minus: see the half-cycle shift above
-            accd[2 * p + 1] -= (double) st[p].acci;
-            st[p].accr = st[p].acci = 0.f;
+            float px_, py_, qx_, qy_;
+            unpack2(st[p].accp, px_, py_);
+            unpack2(st[p].accq, qx_, qy_);
+            accd[2 * p] -= (double) (px_ - qy_);
+            accd[2 * p + 1] -= (double) (py_ + qx_);
+            st[p].accp = st[p].accq = 0ull;
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&hdr->empty[s]);
@@ -463,7 +532,7 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, FastParams P,
             acc[gidx[p]] = a;
         }
     }
-    if (overflow) status->window_overflow = 1;
+    if (jjmax > jmax) status->window_overflow = 1;
 }
 
 // ---- host side: polynomial fit of the tap weights ---------------------------------------
@@ -474,6 +543,7 @@ struct FitResult {
     double max_err;
     float even[MAX_TAPS / 2 + 1][MAX_COEF / 2];
     float odd[MAX_TAPS / 2 + 1][MAX_COEF / 2];
+    TapPoly rows[MAX_TAPS / 2 + 1];
 };
 
 // least squares fit of y(g), g in [-1,1], by Chebyshev-node sampling + normal equations in a
@@ -550,6 +620,11 @@ static FitResult fit_kernel(const DevKernel& k, double tol)
                 worst = std::max(worst, std::fabs(wm - (double) kernel_eval(k, -cm - (double) f)));
         }
     }
+    for (int m = 0; m < nh; ++m)
+        for (int i = 0; i < MAX_COEF / 2; ++i) {
+            R.rows[m].e[i] = R.even[m][i];
+            R.rows[m].o[i] = R.odd[m][i];
+        }
     R.max_err = worst;
     R.ok = worst <= tol;
     return R;
@@ -595,12 +670,12 @@ static EncodeTiledFn get_encode_fn()
     return fn;
 }
 
-template<int K, int D>
+template<int K, int D, int UNROLL>
 static int launch_inst(const CUtensorMap& map, const FastParams& FP, const PixelRec* pix,
                        const PulseRec* pulse, double2* acc, unsigned char* tile_generic,
                        DevStatus* status, size_t smem, cudaStream_t s)
 {
-    auto kern = accumulate_fast_kernel<K, D>;
+    auto kern = accumulate_fast_kernel<K, D, UNROLL>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess) return (int) e;
     const unsigned grid = (unsigned) (FP.tiles_rg * FP.tiles_az);
@@ -639,9 +714,7 @@ int launch_accumulate_fast(const AccumParams& P, const DevKernel& hk, const Pixe
     if (cr != CUDA_SUCCESS) return -1;
 
     cudaError_t e;
-    e = cudaMemcpyToSymbolAsync(c_even, R.even, sizeof(R.even), 0, cudaMemcpyHostToDevice, s);
-    if (e != cudaSuccess) return (int) e;
-    e = cudaMemcpyToSymbolAsync(c_odd, R.odd, sizeof(R.odd), 0, cudaMemcpyHostToDevice, s);
+    e = cudaMemcpyToSymbolAsync(c_poly, R.rows, sizeof(R.rows), 0, cudaMemcpyHostToDevice, s);
     if (e != cudaSuccess) return (int) e;
 
     FastParams FP;
@@ -661,11 +734,17 @@ int launch_accumulate_fast(const AccumParams& P, const DevKernel& hk, const Pixe
     FP.U0 = P.swst / P.dtau;
     FP.fc = P.fc;
     const size_t smem = HEADER_BYTES + NSTAGE * stage_bytes(W) + (size_t) NTHREADS * 2 * PX * sizeof(double);
+    static const int unroll2 = [] {
+        const char* e = std::getenv("I3B_FAST_UNROLL"); // tuning knob (default 1)
+        return e && std::atoi(e) == 2;
+    }();
     switch (K) {
-    case 8: return launch_inst<8, 7>(map, FP, pix, pulse, acc, tile_generic, status, smem, s);
-    case 9: return launch_inst<9, 6>(map, FP, pix, pulse, acc, tile_generic, status, smem, s);
-    case 16: return launch_inst<16, 7>(map, FP, pix, pulse, acc, tile_generic, status, smem, s);
-    case 32: return launch_inst<32, 7>(map, FP, pix, pulse, acc, tile_generic, status, smem, s);
+    case 8: return launch_inst<8, 7, 1>(map, FP, pix, pulse, acc, tile_generic, status, smem, s);
+    case 9:
+        return unroll2 ? launch_inst<9, 6, 2>(map, FP, pix, pulse, acc, tile_generic, status, smem, s)
+                       : launch_inst<9, 6, 1>(map, FP, pix, pulse, acc, tile_generic, status, smem, s);
+    case 16: return launch_inst<16, 7, 1>(map, FP, pix, pulse, acc, tile_generic, status, smem, s);
+    case 32: return launch_inst<32, 7, 1>(map, FP, pix, pulse, acc, tile_generic, status, smem, s);
     default: return -1;
     }
 }

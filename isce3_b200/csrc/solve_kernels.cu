@@ -14,16 +14,21 @@ namespace i3b {
 __global__ void pulse_table_kernel(DevOrbit orbit, Linspace in_time, double fc, PulseRec* pulse,
                                    double* pv, DevStatus* status)
 {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= in_time.size) return;
+    const int kt = blockIdx.x * blockDim.x + threadIdx.x;
+    if (kt >= in_time.size + kPulseTablePad) return;
+    // entries past the last pulse replicate it: the fast kernel's staged tiles may run
+    // over the end of the table and must keep sane geometry there (results are discarded)
+    const int k = min(kt, in_time.size - 1);
     D3 p, v;
     const int st = orbit_interpolate(orbit, in_time[k], BORDER_ERROR, &p, &v);
     if (st != I3B_SUCCESS) {
         status->hard_error = I3B_EXC_OUT_OF_RANGE;
         p = v = nan3();
     }
-    pv[6 * k + 0] = p.x; pv[6 * k + 1] = p.y; pv[6 * k + 2] = p.z;
-    pv[6 * k + 3] = v.x; pv[6 * k + 4] = v.y; pv[6 * k + 5] = v.z;
+    if (kt < in_time.size) {
+        pv[6 * k + 0] = p.x; pv[6 * k + 1] = p.y; pv[6 * k + 2] = p.z;
+        pv[6 * k + 3] = v.x; pv[6 * k + 4] = v.y; pv[6 * k + 5] = v.z;
+    }
     const double A = 2.0 / (dot(v, v) - kC * kC);
     PulseRec r;
     r.m2px = -2.0 * p.x; r.m2py = -2.0 * p.y; r.m2pz = -2.0 * p.z;
@@ -33,7 +38,7 @@ __global__ void pulse_table_kernel(DevOrbit orbit, Linspace in_time, double fc, 
     r.E = -fA * dot(p, v);
     r.Cs = -fA * kC;
     r.pad = 0.0;
-    pulse[k] = r;
+    pulse[kt] = r;
 }
 
 // ---- per-pixel target solve -------------------------------------------------------
@@ -186,7 +191,7 @@ __global__ void finalize_kernel(long long npix, const PixelRec* __restrict__ pix
 void launch_pulse_table(const DevOrbit& orbit, Linspace in_time, double fc, PulseRec* pulse,
                         double* pv, DevStatus* status, cudaStream_t s)
 {
-    const int n = in_time.size;
+    const int n = in_time.size + kPulseTablePad;
     pulse_table_kernel<<<(n + 127) / 128, 128, 0, s>>>(orbit, in_time, fc, pulse, pv, status);
 }
 
