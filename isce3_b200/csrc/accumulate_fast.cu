@@ -39,12 +39,22 @@
 namespace i3b {
 
 constexpr int TILE_RG = 128;  // output range pixels per CTA tile
-constexpr int TILE_AZ = 4;    // output azimuth lines per CTA tile
+#ifndef I3B_TILE_AZ
+#define I3B_TILE_AZ 4
+#endif
+#ifndef I3B_NSTAGE
+#define I3B_NSTAGE 4
+#endif
+constexpr int TILE_AZ = I3B_TILE_AZ;   // output azimuth lines per CTA tile
 constexpr int PX = 2;         // pixels per thread (range-adjacent)
 constexpr int NTHREADS = TILE_AZ * TILE_RG / PX; // 256 threads; warp 0 is also the producer
 constexpr int TK = 16;        // pulses per stage
-constexpr int NSTAGE = 3;
-constexpr int HEADER_BYTES = 256;
+constexpr int NSTAGE = I3B_NSTAGE;
+constexpr int POLY_OFFSET = 256;   // per-tap polynomial rows (copied from constant memory)
+constexpr int HEADER_BYTES = 1024; // barriers, window origins, corner pixels, polynomial rows
+#ifndef I3B_POLY_SMEM
+#define I3B_POLY_SMEM 0
+#endif
 constexpr int MAX_TAPS = 32;
 constexpr int MAX_COEF = 8;   // degree <= 7
 
@@ -139,7 +149,7 @@ struct SmemHeader {
     double corner[4][4]; // x, y, z, fc*tau_atm of the 4 corner pixels
 };
 
-static_assert(sizeof(SmemHeader) <= HEADER_BYTES, "shared-memory header overflows its slot");
+static_assert(sizeof(SmemHeader) <= POLY_OFFSET, "shared-memory header overflows its slot");
 
 __host__ __device__ inline size_t stage_bytes(int W)
 {
@@ -209,7 +219,7 @@ template<int K, int D>
 struct Weights {
     // Tap weights of TWO pixels at once: f = (f_pixel0, f_pixel1) in [-0.5, 0.5);
     // w[m] = (w_m(f0), w_m(f1)).  Coefficients enter as scalar-broadcast operands.
-    __device__ static __forceinline__ void eval(f32x2 f, f32x2 (&w)[K])
+    __device__ static __forceinline__ void eval(f32x2 f, f32x2 (&w)[K], uint32_t poly_addr)
     {
         constexpr int NE = D / 2 + 1;       // even coefficients  f^0, f^2, ...
         constexpr int NO = (D + 1) / 2;     // odd coefficients   f^1, f^3, ...
@@ -217,8 +227,13 @@ struct Weights {
         const f32x2 nf = mul2(f, bcast2(-1.0f));
 #pragma unroll
         for (int m = 0; m < K / 2; ++m) {
+#if I3B_POLY_SMEM
+            // broadcast LDS.128: one wavefront each, no constant-cache (LDC.64) round trips
+            const float4 ce = lds128(poly_addr + 32u * m), co = lds128(poly_addr + 32u * m + 16u);
+#else
             const float4 ce = *reinterpret_cast<const float4*>(c_poly[m].e);
             const float4 co = *reinterpret_cast<const float4*>(c_poly[m].o);
+#endif
             const float cev[4] = {ce.x, ce.y, ce.z, ce.w}, cov[4] = {co.x, co.y, co.z, co.w};
             f32x2 e = bcast2(cev[NE - 1]);
 #pragma unroll
@@ -231,7 +246,11 @@ struct Weights {
         }
         if (K & 1) {
             constexpr int m = K / 2;
+#if I3B_POLY_SMEM
+            const float4 ce = lds128(poly_addr + 32u * m);
+#else
             const float4 ce = *reinterpret_cast<const float4*>(c_poly[m].e);
+#endif
             const float cev[4] = {ce.x, ce.y, ce.z, ce.w};
             f32x2 e = bcast2(cev[NE - 1]);
 #pragma unroll
@@ -270,6 +289,10 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, FastParams P,
     constexpr int LOWOFF = (K & 1) ? -(K / 2) : 1 - K / 2;
     constexpr double SHIFT = (K & 1) ? 0.5 : 0.0;
 
+    static_assert(POLY_OFFSET + sizeof(TapPoly) * (MAX_TAPS / 2 + 1) <= HEADER_BYTES, "header too small");
+    if (tid < (int) (sizeof(TapPoly) * (K / 2 + 1) / sizeof(float)))
+        reinterpret_cast<float*>(smem_raw + POLY_OFFSET)[tid] = reinterpret_cast<const float*>(c_poly)[tid];
+    const uint32_t poly_addr = smem_u32(smem_raw + POLY_OFFSET);
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; ++s) {
             mbar_init(&hdr->full[s], 1);
@@ -459,7 +482,7 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, FastParams P,
             }
             const uint32_t line_addr = lines_addr + (uint32_t) kk * row_bytes;
             f32x2 w[K];
-            Weights<K, D>::eval(pack2(f[0], f[1]), w);
+            Weights<K, D>::eval(pack2(f[0], f[1]), w, poly_addr);
             float w0[K], w1[K];
 #pragma unroll
             for (int m = 0; m < K; ++m) unpack2(w[m], w0[m], w1[m]);
