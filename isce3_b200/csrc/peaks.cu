@@ -72,6 +72,8 @@ __global__ void __launch_bounds__(256) peak_mufu_kernel(float* out, float a, lon
     float x[PEAK_CHAINS];
 #pragma unroll
     for (int i = 0; i < PEAK_CHAINS; ++i) x[i] = threadIdx.x * 1e-3f + i * 0.1f;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     const long long c0 = clock64();
     for (int it = 0; it < PEAK_ITERS; ++it) {
 #pragma unroll
@@ -81,11 +83,15 @@ __global__ void __launch_bounds__(256) peak_mufu_kernel(float* out, float a, lon
         }
     }
     const long long c1 = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < PEAK_CHAINS; ++i) s += x[i];
     if (s == 12345.678f) out[0] = s;
-    if (blockIdx.x == 0 && threadIdx.x == 0) clocks[0] = c1 - c0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        clocks[0] = c1 - c0;              // SM cycles ...
+        clocks[1] = (long long) (t1 - t0); // ... over this many nanoseconds
+    }
 }
 
 template<class L>
@@ -142,13 +148,9 @@ int measure_peaks(int device, I3B_Peaks* out)
     rc = time_kernel([&]() { peak_mufu_kernel<<<grid, block>>>(d_out, 0.001f, d_clk); }, &ms);
     if (rc) return rc;
     out->sfu_gops = ops / (ms * 1e-3) / 1e9;
-    long long clk = 0;
-    cudaMemcpy(&clk, d_clk, sizeof clk, cudaMemcpyDeviceToHost);
-    // block 0 ran `clk` cycles for 1/(waves) of the kernel: grid/sm_count/occupancy waves
-    int occ = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, peak_mufu_kernel, block, 0);
-    const double waves = std::max(1.0, (double) grid / (prop.multiProcessorCount * std::max(occ, 1)));
-    out->sm_mhz = (double) clk * waves / (ms * 1e-3) / 1e6;
+    long long clk[2] = {0, 0};
+    cudaMemcpy(clk, d_clk, sizeof clk, cudaMemcpyDeviceToHost);
+    out->sm_mhz = clk[1] > 0 ? (double) clk[0] / (double) clk[1] * 1e3 : 0.0; // cycles per ns -> MHz
     out->_pad = (int) (ffma2 > ffma); // 1 when the packed form was the faster one
     cudaFree(d_out);
     cudaFree(d_clk);
