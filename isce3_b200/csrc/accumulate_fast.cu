@@ -51,6 +51,10 @@ constexpr int NTHREADS = TILE_AZ * TILE_RG / PX; // 256 threads; warp 0 is also 
 constexpr int TK = 16;        // pulses per stage
 constexpr int NSTAGE = I3B_NSTAGE;
 constexpr int POLY_OFFSET = 256;   // per-tap polynomial rows (copied from constant memory)
+#ifndef I3B_ROTATE_PRODUCER
+#define I3B_ROTATE_PRODUCER 1
+#endif
+constexpr int NWARPS_ROT = TILE_AZ * TILE_RG / 2 / 32;
 constexpr int HEADER_BYTES = 1024; // barriers, window origins, corner pixels, polynomial rows
 #ifndef I3B_POLY_SMEM
 #define I3B_POLY_SMEM 0
@@ -437,7 +441,9 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, FastParams P,
     const unsigned jmax = (unsigned) (P.W - (K + 3));
 
     for (int n = 0; n < ntiles; ++n) {
-        if (warp == 0 && n + NSTAGE - 1 < ntiles) produce(n + NSTAGE - 1);
+        // the producer duty rotates over the warps so that no warp is systematically slower
+        // (a fixed producer warp paces the whole CTA through the full/empty barriers)
+        if (n + NSTAGE - 1 < ntiles && warp == (I3B_ROTATE_PRODUCER ? (n + NSTAGE - 1) % NWARPS_ROT : 0)) produce(n + NSTAGE - 1);
         const int s = n % NSTAGE;
         mbar_wait(&hdr->full[s], (n / NSTAGE) & 1);
         const uint32_t lines_addr = stage_addr0 + (uint32_t) s * (uint32_t) sbytes;
@@ -722,6 +728,9 @@ int launch_accumulate_fast(const AccumParams& P, const DevKernel& hk, const Pixe
     if (!R.ok || !taps_supported(hk.taps)) return -1;
     const int K = hk.taps;
     int W = (int) std::ceil(TILE_RG * std::fabs(out_in_spacing_ratio) * 1.002) + K + 16;
+#ifdef I3B_EXTRA_W
+    W += I3B_EXTRA_W; // experiment: stage more samples than needed (TMA sensitivity)
+#endif
     W = (W + 1) & ~1;
     if (W > 256) return -1;
     EncodeTiledFn enc = get_encode_fn();
