@@ -157,7 +157,7 @@ static_assert(sizeof(SmemHeader) <= POLY_OFFSET, "shared-memory header overflows
 
 __host__ __device__ inline size_t stage_bytes(int W)
 {
-    size_t b = (size_t) TK * W * sizeof(float2) + (size_t) TK * sizeof(PulseRec);
+    size_t b = (size_t) TK * W * sizeof(float2);
     return (b + 127) & ~(size_t) 127;
 }
 
@@ -264,15 +264,29 @@ struct Weights {
     }
 };
 
-// Per-pixel loop state.
+// Per-pixel loop state (all FP32 / int: the FP64 geometry lives at segment boundaries only).
 struct PixState {
-    double x, y, z, xx;   // target position, |x|^2
-    double s1, s2, yh;    // range at the two previous pulses; 0.5 / range
-    double upix;          // fc*tau_atm*G - U0 + shift
-    double mphase;        // MAGIC + fc*tau_atm
-    f32x2 accp, accq;     // FP32 partial sums of the pulse tile: sum cos*(ar,ai), sum sin*(ar,ai)
-    int kstart, kspan;    // aperture: kstart <= k < kstart + kspan
+    float ang0;        // 2*pi*(carrier phase in cycles at the segment base, reduced to [-1/2, 1/2])
+    float f0m;         // frac(sample coordinate at the segment base) - 1/2
+    float c1, c2, c3;  // carrier phase increment over the segment: ((c3 j + c2) j + c1) j  [rad]
+    int i0rel;         // window start at the base, relative to the staged tile, minus the magic bias
+    f32x2 accp, accq;  // FP32 partial sums of the pulse tile: sum cos*(re,im), sum sin*(re,im)
+    int kstart, kspan; // aperture: kstart <= k < kstart + kspan
 };
+
+constexpr int SEG = 32; // pulses per geometry segment
+static_assert(SEG % TK == 0, "a geometry segment is a whole number of staged pulse tiles");
+constexpr float MAGIC32 = 12582912.0f;         // 1.5 * 2^23: float -> nearest integer by addition
+constexpr int MAGIC32_BITS = 0x4B400000;
+
+// exact carrier phase (cycles, incl. troposphere) of one pixel at one pulse, FP64
+__device__ __forceinline__ double exact_cycles(const PixelRec& q, double xx, double t0cyc,
+                                               const PulseRec& r)
+{
+    const double r2 = fma(q.x, r.m2px, fma(q.y, r.m2py, fma(q.z, r.m2pz, xx + r.pp)));
+    const double sr = sqrt(r2);
+    return fma(r.Cs, sr, fma(q.x, r.vBx, fma(q.y, r.vBy, fma(q.z, r.vBz, t0cyc + r.E))));
+}
 
 template<int K, int D, int UNROLL>
 __global__ void __launch_bounds__(NTHREADS, 2)
@@ -293,10 +307,6 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, FastParams P,
     constexpr int LOWOFF = (K & 1) ? -(K / 2) : 1 - K / 2;
     constexpr double SHIFT = (K & 1) ? 0.5 : 0.0;
 
-    static_assert(POLY_OFFSET + sizeof(TapPoly) * (MAX_TAPS / 2 + 1) <= HEADER_BYTES, "header too small");
-    if (tid < (int) (sizeof(TapPoly) * (K / 2 + 1) / sizeof(float)))
-        reinterpret_cast<float*>(smem_raw + POLY_OFFSET)[tid] = reinterpret_cast<const float*>(c_poly)[tid];
-    const uint32_t poly_addr = smem_u32(smem_raw + POLY_OFFSET);
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; ++s) {
             mbar_init(&hdr->full[s], 1);
@@ -311,11 +321,10 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, FastParams P,
 
     // ---- prologue: pixel records, CTA pulse range, corner positions ----------------
     PixState st[PX];
-    bool in_grid[PX];
     long long gidx[PX];
+    const int lrow = tid / (TILE_RG / PX);
+    const int lcol = (tid % (TILE_RG / PX)) * PX;
     {
-        const int lrow = tid / (TILE_RG / PX);
-        const int lcol = (tid % (TILE_RG / PX)) * PX;
         const int last_row = min(TILE_AZ, P.out_lines - line0) - 1;
         const int last_col = min(TILE_RG, P.out_width - col0) - 1;
         int kmin = INT_MAX, kmax = INT_MIN;
@@ -323,18 +332,13 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, FastParams P,
 #pragma unroll
         for (int p = 0; p < PX; ++p) {
             const int jj = line0 + lrow, ii = col0 + lcol + p;
-            in_grid[p] = (jj < P.out_lines) && (ii < P.out_width);
+            const bool in_grid = (jj < P.out_lines) && (ii < P.out_width);
             const int jc = min(jj, P.out_lines - 1), ic = min(ii, P.out_width - 1);
             gidx[p] = (long long) jc * P.out_width + ic;
             const PixelRec r = pix[gidx[p]];
             if (r.kstart < 0) bad = true;
-            st[p].x = r.x; st[p].y = r.y; st[p].z = r.z;
-            st[p].xx = r.x * r.x + r.y * r.y + r.z * r.z;
-            const double t0cyc = P.fc * r.tau_atm;
-            st[p].upix = fma(t0cyc, P.G, SHIFT - P.U0);
-            st[p].mphase = MAGIC + t0cyc;
-            const int ks = in_grid[p] ? max(r.kstart, P.k_begin) : 0;
-            const int ke_p = in_grid[p] ? min(r.kstop, P.k_end) : 0;
+            const int ks = in_grid ? max(r.kstart, P.k_begin) : 0;
+            const int ke_p = in_grid ? min(r.kstop, P.k_end) : 0;
             st[p].kstart = ks;
             st[p].kspan = max(ke_p - ks, 0);
             st[p].accp = st[p].accq = 0ull;
@@ -351,7 +355,7 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, FastParams P,
                 const bool rsel = (c & 2) ? bot : top, csel = (c & 1) ? rig : lef;
                 if (rsel && csel) {
                     hdr->corner[c][0] = r.x; hdr->corner[c][1] = r.y; hdr->corner[c][2] = r.z;
-                    hdr->corner[c][3] = t0cyc;
+                    hdr->corner[c][3] = P.fc * r.tau_atm;
                 }
             }
         }
@@ -376,12 +380,12 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, FastParams P,
     if (kb >= ke) return; // nothing to integrate in this launch
     const int ntiles = (ke - kb + TK - 1) / TK;
 
-    // Producer role (warp 0, all lanes converge here): stage pulse tile n.
+    // Producer role (one warp, all lanes converge here): stage pulse tile n.
     auto produce = [&](int n) {
         const int s = n % NSTAGE;
         if (n >= NSTAGE) mbar_wait(&hdr->empty[s], ((n / NSTAGE) - 1) & 1);
         const int kfirst = kb + n * TK;
-        const int klast = min(kfirst + TK - 1, P.n_pulses - 1);
+        const int klast = kfirst + TK - 1; // the pulse table is padded past the last pulse
         // range window from the 4 corner pixels at the first/last pulse of the tile
         double u = 0.;
         if (lane < 8) {
@@ -401,12 +405,8 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, FastParams P,
             if (!(umin == umin) || whi - wlo > P.W) status->window_overflow = 1;
             hdr->winlo[s] = wlo;
             unsigned char* sp = stage0 + (size_t) s * sbytes;
-            const uint32_t bytes = (uint32_t) ((size_t) TK * P.W * sizeof(float2) +
-                                               (size_t) TK * sizeof(PulseRec));
-            mbar_arrive_expect_tx(&hdr->full[s], bytes);
+            mbar_arrive_expect_tx(&hdr->full[s], (uint32_t) ((size_t) TK * P.W * sizeof(float2)));
             tma_load_2d(sp, &rc_map, wlo, kfirst - P.rc_k0, &hdr->full[s]);
-            bulk_load_1d(sp + (size_t) TK * P.W * sizeof(float2), pulse + kfirst,
-                         (uint32_t) (TK * sizeof(PulseRec)), &hdr->full[s]);
         }
         __syncwarp();
     };
@@ -414,81 +414,101 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, FastParams P,
         for (int n = 0; n < NSTAGE - 1 && n < ntiles; ++n) produce(n);
     }
 
-    // initial range state: exact sqrt at the two pulses before kb (linear extrapolation
-    // when kb < 2), so the predictor 2*s1 - s2 starts within a second difference of truth.
-    {
-        const int ka = max(kb - 2, 0);
-        const PulseRec ra = pulse[ka], rb = pulse[min(ka + 1, P.n_pulses - 1)];
-#pragma unroll
-        for (int p = 0; p < PX; ++p) {
-            const double r2a = fma(st[p].x, ra.m2px, fma(st[p].y, ra.m2py, fma(st[p].z, ra.m2pz, st[p].xx + ra.pp)));
-            const double r2b = fma(st[p].x, rb.m2px, fma(st[p].y, rb.m2py, fma(st[p].z, rb.m2pz, st[p].xx + rb.pp)));
-            const double sa = sqrt(r2a), sb = sqrt(r2b);
-            const double slope = sb - sa;
-            st[p].s2 = fma(slope, (double) (kb - 2 - ka), sa);
-            st[p].s1 = fma(slope, (double) (kb - 1 - ka), sa);
-            st[p].yh = 0.5 / sa;
-        }
-    }
-    // FP64 running sums live in shared memory (one private slot per thread)
-    double* accd = reinterpret_cast<double*>(smem_raw + HEADER_BYTES + NSTAGE * sbytes) + tid * (2 * PX);
+    // Per-thread shared-memory slots: FP64 running sums (2 per pixel) and the exact carrier
+    // phase at the four segment boundaries around the current segment (4 per pixel).
+    double* slot = reinterpret_cast<double*>(smem_raw + HEADER_BYTES + NSTAGE * sbytes) + tid * (6 * PX);
+    double* accd = slot;          // [2 * PX]
+    double* ybnd = slot + 2 * PX; // [PX][4]  T(b - SEG), T(b), T(b + SEG), T(b + 2 SEG)
 #pragma unroll
     for (int i = 0; i < 2 * PX; ++i) accd[i] = 0.0;
+    // boundaries b_i = kb + SEG * i; evaluate T at b_{-1}, b_0, b_1 (b_2 comes with segment 0)
+#pragma unroll
+    for (int p = 0; p < PX; ++p) {
+        const PixelRec q = pix[gidx[p]];
+        const double xx = q.x * q.x + q.y * q.y + q.z * q.z, t0 = P.fc * q.tau_atm;
+        ybnd[4 * p + 1] = exact_cycles(q, xx, t0, pulse[kb - SEG]);
+        ybnd[4 * p + 2] = exact_cycles(q, xx, t0, pulse[kb]);
+        ybnd[4 * p + 3] = exact_cycles(q, xx, t0, pulse[kb + SEG]);
+    }
+
     unsigned jjmax = 0; // sticky maximum of the (unsigned) window offsets: overflow detector
-    const float TWO_PI = 6.28318530717958647692f, THREE_PI = 9.42477796076937971538f;
     const uint32_t stage_addr0 = smem_u32(stage0);
     const uint32_t row_bytes = (uint32_t) P.W * (uint32_t) sizeof(float2);
     const unsigned jmax = (unsigned) (P.W - (K + 3));
+    const float TWO_PI_F = 6.28318530717958647692f;
+    const double TWO_PI_D = 6.283185307179586476925;
+    const float Gr = (float) (P.G / TWO_PI_D); // samples per radian of carrier phase
+    float jf = 0.f;                             // pulse index within the segment
 
     for (int n = 0; n < ntiles; ++n) {
-        // the producer duty rotates over the warps so that no warp is systematically slower
-        // (a fixed producer warp paces the whole CTA through the full/empty barriers)
-        if (n + NSTAGE - 1 < ntiles && warp == (I3B_ROTATE_PRODUCER ? (n + NSTAGE - 1) % NWARPS_ROT : 0)) produce(n + NSTAGE - 1);
+        if (n + NSTAGE - 1 < ntiles && warp == (I3B_ROTATE_PRODUCER ? (n + NSTAGE - 1) % NWARPS_ROT : 0))
+            produce(n + NSTAGE - 1);
+
+        if ((n % (SEG / TK)) == 0) {
+            // ---- new geometry segment: one exact FP64 evaluation per pixel, cubic through
+            // the four surrounding boundaries, everything inside the segment is FP32 ----
+            const int b = kb + n * TK;
+#pragma unroll
+            for (int p = 0; p < PX; ++p) {
+                const PixelRec q = pix[gidx[p]];
+                const double xx = q.x * q.x + q.y * q.y + q.z * q.z, t0 = P.fc * q.tau_atm;
+                const double y0 = ybnd[4 * p + 1], y1 = ybnd[4 * p + 2], y2 = ybnd[4 * p + 3];
+                const double y3 = exact_cycles(q, xx, t0, pulse[b + 2 * SEG]);
+                ybnd[4 * p + 1] = y1;
+                ybnd[4 * p + 2] = y2;
+                ybnd[4 * p + 3] = y3;
+                const double d1 = y2 - y1, d2 = (y2 - y1) - (y1 - y0);
+                const double d3 = ((y3 - y2) - (y2 - y1)) - d2;
+                // p(tau) - y1 = tau (d1 - d2/2 - d3/6) + tau^2 d2/2 + tau^3 d3/6, tau = j / SEG
+                st[p].c1 = (float) (TWO_PI_D * (d1 - 0.5 * d2 - d3 * (1.0 / 6.0)) * (1.0 / SEG));
+                st[p].c2 = (float) (TWO_PI_D * (0.5 * d2) * (1.0 / (SEG * SEG)));
+                st[p].c3 = (float) (TWO_PI_D * (d3 * (1.0 / 6.0)) * (1.0 / ((double) SEG * SEG * SEG)));
+                st[p].ang0 = (float) (TWO_PI_D * (y1 - rint(y1)));
+                const double uh = fma(y1, P.G, SHIFT - P.U0);
+                const double ufl = floor(uh);
+                st[p].f0m = (float) (uh - ufl) - 0.5f;
+                st[p].i0rel = (int) ufl + LOWOFF - MAGIC32_BITS; // window origin added per tile
+            }
+            jf = 0.f;
+        }
+
         const int s = n % NSTAGE;
         mbar_wait(&hdr->full[s], (n / NSTAGE) & 1);
         const uint32_t lines_addr = stage_addr0 + (uint32_t) s * (uint32_t) sbytes;
-        const uint32_t prec_addr = lines_addr + (uint32_t) TK * row_bytes;
-        // index constant: j0 = (mantissa >> 23) - CONST  (see MAGIC)
-        const unsigned jconst = 0x80000000u + 0x10000000u + (unsigned) hdr->winlo[s] - (unsigned) LOWOFF;
+        const int wlo = hdr->winlo[s];
         // k - kstart for the first pulse of the tile, per pixel
-        unsigned krel0 = (unsigned) (kb + n * TK - st[0].kstart);
-        unsigned krel1 = (unsigned) (kb + n * TK - st[1].kstart);
+        const unsigned krel0 = (unsigned) (kb + n * TK - st[0].kstart);
+        const unsigned krel1 = (unsigned) (kb + n * TK - st[1].kstart);
 
 #pragma unroll UNROLL
         for (int kk = 0; kk < TK; ++kk) {
-            const uint32_t pa = prec_addr + (uint32_t) kk * (uint32_t) sizeof(PulseRec);
-            const double2 c0 = lds_d2(pa), c1 = lds_d2(pa + 16), c2 = lds_d2(pa + 32),
-                          c3 = lds_d2(pa + 48), c4 = lds_d2(pa + 64);
-            // PulseRec: m2px m2py | m2pz pp | vBx vBy | vBz E | Cs pad
             float f[PX], cs[PX], sn[PX];
             unsigned j0[PX];
 #pragma unroll
             for (int p = 0; p < PX; ++p) {
-                PixState& q = st[p];
-                const double r2 = fma(q.x, c0.x, fma(q.y, c0.y, fma(q.z, c1.x, q.xx + c1.y)));
-                const double spred = fma(2.0, q.s1, -q.s2);
-                const double e = fma(-spred, spred, r2);
-                const double sv = fma(e, q.yh, spred);
-                q.s2 = q.s1;
-                q.s1 = sv;
-                const double tgeo = fma(c4.x, sv, fma(q.x, c2.x, fma(q.y, c2.y, fma(q.z, c3.x, c3.y))));
-                const double mu = fma(tgeo, P.G, q.upix) + MAGIC;
-                const double mt = tgeo + q.mphase;
-                const unsigned ulo = (unsigned) __double2loint(mu), uhi = (unsigned) __double2hiint(mu);
-                f[p] = __uint_as_float((ulo & 0x007FFFFFu) | 0x3F800000u) - 1.5f;
-                const unsigned jj = __funnelshift_r(ulo, uhi, 23) - jconst;
+                const PixState& q = st[p];
+                const float t = fmaf(fmaf(q.c3, jf, q.c2), jf, q.c1);
+                const float qr = t * jf;            // carrier phase increment since the base [rad]
+                const float ang = qr + q.ang0;
+                const float g = fmaf(qr, Gr, q.f0m); // sample coordinate - floor(base) - 1/2
+                const float m = g + MAGIC32;         // nearest integer of g == floor(coordinate)
+                f[p] = g - (m - MAGIC32);            // centred fraction in [-1/2, 1/2]
+                const unsigned jj = (unsigned) (q.i0rel + __float_as_int(m) - wlo);
                 jjmax = max(jjmax, jj);
                 j0[p] = min(jj, jmax);
-                const unsigned tlo = (unsigned) __double2loint(mt);
-                const float v = __uint_as_float((tlo & 0x007FFFFFu) | 0x3F800000u);
-                const float ang = fmaf(v, TWO_PI, -THREE_PI); // 2*pi*(frac - 0.5)
-                // cos/sin(2 pi frac) = -cos/-sin(ang); the sign is applied at the flush
-                cs[p] = __cosf(ang);
-                sn[p] = __sinf(ang);
+                // outside the pixel's aperture the rotation is zero: nothing accumulates
+                const bool inside = (p == 0 ? krel0 : krel1) + (unsigned) kk < (unsigned) q.kspan;
+                cs[p] = 0.f;
+                sn[p] = 0.f;
+                if (inside) {
+                    cs[p] = __cosf(ang);
+                    sn[p] = __sinf(ang);
+                }
             }
+            jf += 1.0f;
             const uint32_t line_addr = lines_addr + (uint32_t) kk * row_bytes;
             f32x2 w[K];
-            Weights<K, D>::eval(pack2(f[0], f[1]), w, poly_addr);
+            Weights<K, D>::eval(pack2(f[0], f[1]), w, 0u);
             float w0[K], w1[K];
 #pragma unroll
             for (int m = 0; m < K; ++m) unpack2(w[m], w0[m], w1[m]);
@@ -528,25 +548,21 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, FastParams P,
                     a1 = fma2(bcast2(w1[m]), lds64(s1 + 8u * m), a1);
                 }
             }
-            // rotate by the carrier phase and accumulate, only inside the pixel's aperture
-            if (krel0 + kk < (unsigned) st[0].kspan) {
-                st[0].accp = fma2(bcast2(cs[0]), a0, st[0].accp);
-                st[0].accq = fma2(bcast2(sn[0]), a0, st[0].accq);
-            }
-            if (krel1 + kk < (unsigned) st[1].kspan) {
-                st[1].accp = fma2(bcast2(cs[1]), a1, st[1].accp);
-                st[1].accq = fma2(bcast2(sn[1]), a1, st[1].accq);
-            }
+            // rotate by the carrier phase and accumulate (zero rotation outside the aperture)
+            st[0].accp = fma2(bcast2(cs[0]), a0, st[0].accp);
+            st[0].accq = fma2(bcast2(sn[0]), a0, st[0].accq);
+            st[1].accp = fma2(bcast2(cs[1]), a1, st[1].accp);
+            st[1].accq = fma2(bcast2(sn[1]), a1, st[1].accq);
         }
         // pulse tile done: fold FP32 partials into FP64, release the stage.
-        // sum s*e^{j phi} = (P.x - Q.y) + j (P.y + Q.x), negated (half-cycle shift above)
+        // sum s*e^{j phi} = (P.x - Q.y) + j (P.y + Q.x)
 #pragma unroll
         for (int p = 0; p < PX; ++p) {
             float px_, py_, qx_, qy_;
             unpack2(st[p].accp, px_, py_);
             unpack2(st[p].accq, qx_, qy_);
-            accd[2 * p] -= (double) (px_ - qy_);
-            accd[2 * p + 1] -= (double) (py_ + qx_);
+            accd[2 * p] += (double) (px_ - qy_);
+            accd[2 * p + 1] += (double) (py_ + qx_);
             st[p].accp = st[p].accq = 0ull;
         }
         __syncwarp();
@@ -554,7 +570,8 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, FastParams P,
     }
 #pragma unroll
     for (int p = 0; p < PX; ++p) {
-        if (in_grid[p]) {
+        const int jj = line0 + lrow, ii = col0 + lcol + p;
+        if (jj < P.out_lines && ii < P.out_width) {
             double2 a = acc[gidx[p]];
             a.x += accd[2 * p];
             a.y += accd[2 * p + 1];
@@ -765,7 +782,7 @@ int launch_accumulate_fast(const AccumParams& P, const DevKernel& hk, const Pixe
     FP.G = 1.0 / (P.fc * P.dtau);
     FP.U0 = P.swst / P.dtau;
     FP.fc = P.fc;
-    const size_t smem = HEADER_BYTES + NSTAGE * stage_bytes(W) + (size_t) NTHREADS * 2 * PX * sizeof(double);
+    const size_t smem = HEADER_BYTES + NSTAGE * stage_bytes(W) + (size_t) NTHREADS * 6 * PX * sizeof(double);
     static const int unroll2 = [] {
         const char* e = std::getenv("I3B_FAST_UNROLL"); // tuning knob (default 1)
         return e && std::atoi(e) == 2;

@@ -287,7 +287,7 @@ static void shard_setup(const HostScene& hs, Shard& sh)
 
     const size_t npix = (size_t) sh.nlines * og.grid.width;
     const int n_pulses = (int) ig.grid.length;
-    sh.pulse.alloc((size_t) n_pulses + kPulseTablePad);
+    sh.pulse.alloc((size_t) n_pulses + kPulsePadLo + kPulsePadHi);
     CK(cudaMemsetAsync(sh.pulse.p, 0, sh.pulse.n * sizeof(PulseRec), s));
     sh.pv.alloc((size_t) 6 * std::max(n_pulses, 1));
     sh.status.alloc(1);
@@ -330,7 +330,7 @@ static void shard_solve(const HostScene& hs, Shard& sh)
     CK(cudaMemcpyAsync(sh.status.p, &init, sizeof init, cudaMemcpyHostToDevice, s));
     Event e0, e1;
     e0.record(s);
-    launch_pulse_table(sh.sp.in_orbit, sh.sp.in_time, hs.a.fc, sh.pulse.p, sh.pv.p, sh.status.p, s);
+    launch_pulse_table(sh.sp.in_orbit, sh.sp.in_time, hs.a.fc, sh.pulse.p + kPulsePadLo, sh.pv.p, sh.status.p, s);
     CK(cudaGetLastError());
     if (sh.ap.npix > 0) {
         launch_target_solve(sh.sp, sh.pix.p, sh.height.p, sh.status.p, s);
@@ -366,7 +366,7 @@ static void shard_accumulate(Shard& sh, int k0, int k1, cudaStream_t s)
     bool done = false;
     if (sh.use_fast) {
         CK(cudaMemsetAsync(sh.tile_mask.p, 0, sh.tile_mask.n, s));
-        const int rc = launch_accumulate_fast(A, sh.host_kernel, sh.pix.p, sh.pulse.p, sh.rc_dev,
+        const int rc = launch_accumulate_fast(A, sh.host_kernel, sh.pix.p, sh.pulse.p + kPulsePadLo, sh.rc_dev,
                                               sh.acc.p, sh.tile_mask.p, sh.status.p, s);
         if (rc > 0) CK((cudaError_t) rc);
         if (rc == 0) {

@@ -54,7 +54,11 @@ int launch_accumulate_fast(const AccumParams& P, const DevKernel& host_kernel,
                            cudaStream_t s);
 int fast_tiles(int out_lines, int out_width);
 void fast_tile_shape(int* tile_az, int* tile_rg);
-constexpr int kPulseTablePad = 64; // zeroed PulseRec entries past the last pulse
+// The pulse table holds records for pulses [-kPulsePadLo, n_pulses + kPulsePadHi): the entries
+// outside the input grid are orbit EXTRAPOLATIONS (smooth continuation), used by the fast
+// kernel's segment-boundary evaluations and by staged tiles that run over the ends.
+constexpr int kPulsePadLo = 64;
+constexpr int kPulsePadHi = 160;
 
 int measure_peaks(int device, I3B_Peaks* out);
 

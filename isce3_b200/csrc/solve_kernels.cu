@@ -14,18 +14,19 @@ namespace i3b {
 __global__ void pulse_table_kernel(DevOrbit orbit, Linspace in_time, double fc, PulseRec* pulse,
                                    double* pv, DevStatus* status)
 {
-    const int kt = blockIdx.x * blockDim.x + threadIdx.x;
-    if (kt >= in_time.size + kPulseTablePad) return;
-    // entries past the last pulse replicate it: the fast kernel's staged tiles may run
-    // over the end of the table and must keep sane geometry there (results are discarded)
-    const int k = min(kt, in_time.size - 1);
+    // pulse[] is indexed from -kPulsePadLo (the pointer passed in is already offset)
+    const int k = (int) (blockIdx.x * blockDim.x + threadIdx.x) - kPulsePadLo;
+    if (k >= in_time.size + kPulsePadHi) return;
+    const bool in_grid = k >= 0 && k < in_time.size;
     D3 p, v;
-    const int st = orbit_interpolate(orbit, in_time[k], BORDER_ERROR, &p, &v);
+    // pulses of the input grid: border mode Error like Backproject.cpp:101-106; padding
+    // entries: smooth orbit extrapolation (never contributes to a pixel)
+    const int st = orbit_interpolate(orbit, in_time[k], in_grid ? BORDER_ERROR : BORDER_EXTRAPOLATE, &p, &v);
     if (st != I3B_SUCCESS) {
-        status->hard_error = I3B_EXC_OUT_OF_RANGE;
+        if (in_grid) status->hard_error = I3B_EXC_OUT_OF_RANGE;
         p = v = nan3();
     }
-    if (kt < in_time.size) {
+    if (in_grid) {
         pv[6 * k + 0] = p.x; pv[6 * k + 1] = p.y; pv[6 * k + 2] = p.z;
         pv[6 * k + 3] = v.x; pv[6 * k + 4] = v.y; pv[6 * k + 5] = v.z;
     }
@@ -38,7 +39,7 @@ __global__ void pulse_table_kernel(DevOrbit orbit, Linspace in_time, double fc, 
     r.E = -fA * dot(p, v);
     r.Cs = -fA * kC;
     r.pad = 0.0;
-    pulse[kt] = r;
+    pulse[k] = r;
 }
 
 // ---- per-pixel target solve -------------------------------------------------------
@@ -191,7 +192,7 @@ __global__ void finalize_kernel(long long npix, const PixelRec* __restrict__ pix
 void launch_pulse_table(const DevOrbit& orbit, Linspace in_time, double fc, PulseRec* pulse,
                         double* pv, DevStatus* status, cudaStream_t s)
 {
-    const int n = in_time.size + kPulseTablePad;
+    const int n = in_time.size + kPulsePadLo + kPulsePadHi;
     pulse_table_kernel<<<(n + 127) / 128, 128, 0, s>>>(orbit, in_time, fc, pulse, pv, status);
 }
 
