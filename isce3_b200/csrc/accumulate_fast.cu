@@ -54,6 +54,17 @@ constexpr int POLY_OFFSET = 256;   // per-tap polynomial rows (copied from const
 #ifndef I3B_ROTATE_PRODUCER
 #define I3B_ROTATE_PRODUCER 1
 #endif
+// Pulse tiles are requested I3B_PREFETCH_DIST tiles ahead.  With NSTAGE - 2 the stage being
+// refilled was consumed TWO tiles ago, so the producing warp practically never waits for
+// the slower warps of the CTA (with NSTAGE - 1 it waited ~15 % of its time, ncu r01 v4).
+#ifndef I3B_PREFETCH_DIST
+#define I3B_PREFETCH_DIST (I3B_NSTAGE - 2)
+#endif
+constexpr int PREFETCH = I3B_PREFETCH_DIST;
+#ifndef I3B_EDGE_SPLIT
+#define I3B_EDGE_SPLIT 1
+#endif
+static_assert(PREFETCH >= 1 && PREFETCH < I3B_NSTAGE, "prefetch distance must be in [1, NSTAGE)");
 constexpr int NWARPS_ROT = TILE_AZ * TILE_RG / 2 / 32;
 constexpr int HEADER_BYTES = 1024; // barriers, window origins, corner pixels, polynomial rows
 #ifndef I3B_POLY_SMEM
@@ -149,7 +160,8 @@ struct SmemHeader {
     int winlo[NSTAGE];
     int kb, ke;     // CTA pulse range
     int bad;        // tile holds a failed pixel -> generic kernel
-    int pad;
+    int ks_max, ke_min; // every pixel of the CTA integrates pulses [ks_max, ke_min)
+    int pad[3];
     double corner[4][4]; // x, y, z, fc*tau_atm of the 4 corner pixels
 };
 
@@ -264,14 +276,29 @@ struct Weights {
     }
 };
 
-// Per-pixel loop state (all FP32 / int: the FP64 geometry lives at segment boundaries only).
-struct PixState {
-    float ang0;        // 2*pi*(carrier phase in cycles at the segment base, reduced to [-1/2, 1/2])
-    float f0m;         // frac(sample coordinate at the segment base) - 1/2
-    float c1, c2, c3;  // carrier phase increment over the segment: ((c3 j + c2) j + c1) j  [rad]
-    int i0rel;         // window start at the base, relative to the staged tile, minus the magic bias
-    f32x2 accp, accq;  // FP32 partial sums of the pulse tile: sum cos*(re,im), sum sin*(re,im)
-    int kstart, kspan; // aperture: kstart <= k < kstart + kspan
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b)
+{
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b)
+{
+    f32x2 d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+// Loop state of a thread's pixel PAIR (all FP32 / int: the FP64 geometry lives at segment
+// boundaries only).  Packed fields hold (pixel 0, pixel 1) so the per-pulse phase / sample
+// coordinate arithmetic of both pixels is one FFMA2 / FADD2 / FMUL2 each.
+struct PairState {
+    f32x2 ang0;        // 2*pi*(carrier phase in cycles at the segment base, reduced to [-1/2, 1/2])
+    f32x2 f0m;         // frac(sample coordinate at the segment base) - 1/2
+    f32x2 c1, c2, c3;  // carrier phase increment over the segment: ((c3 j + c2) j + c1) j  [rad]
+    int i0rel[PX];     // window start at the base minus the magic bias (window origin added per tile)
+    f32x2 accp[PX], accq[PX]; // FP32 partial sums of the pulse tile: sum cos*(re,im), sum sin*(re,im)
+    int kstart[PX], kspan[PX]; // aperture: kstart <= k < kstart + kspan
 };
 
 constexpr int SEG = 32; // pulses per geometry segment
@@ -286,6 +313,112 @@ __device__ __forceinline__ double exact_cycles(const PixelRec& q, double xx, dou
     const double r2 = fma(q.x, r.m2px, fma(q.y, r.m2py, fma(q.z, r.m2pz, xx + r.pp)));
     const double sr = sqrt(r2);
     return fma(r.Cs, sr, fma(q.x, r.vBx, fma(q.y, r.vBy, fma(q.z, r.vBz, t0cyc + r.E))));
+}
+
+#ifndef I3B_MUFU_EARLY
+#define I3B_MUFU_EARLY 0
+#endif
+// sin/cos on the SFU (MUFU after a range-reduction multiply).  The volatile form pins the
+// issue point relative to the (volatile) shared-memory loads of the sample window.
+__device__ __forceinline__ void sincos_fast(float x, float& sn, float& cs)
+{
+#if I3B_MUFU_EARLY
+    asm volatile("sin.approx.ftz.f32 %0, %1;" : "=f"(sn) : "f"(x));
+    asm volatile("cos.approx.ftz.f32 %0, %1;" : "=f"(cs) : "f"(x));
+#else
+    sn = __sinf(x);
+    cs = __cosf(x);
+#endif
+}
+
+// One staged pulse tile (TK pulses) for the thread's pixel pair.  EDGE = false: every pixel
+// of the CTA integrates every pulse of the tile (no aperture test in the loop).
+template<int K, int D, bool EDGE>
+__device__ __forceinline__ void tile_body(PairState& S, float& jf, unsigned& jjmax,
+                                          uint32_t lines_addr, uint32_t row_bytes, int wlo,
+                                          unsigned jmax, float Gr, unsigned krel0, unsigned krel1)
+{
+    const int iw0 = S.i0rel[0] - wlo, iw1 = S.i0rel[1] - wlo;
+    uint32_t line_addr = lines_addr;
+#pragma unroll 1
+    for (int kk = 0; kk < TK; ++kk) {
+        // keep the staged line address a loop-carried register (ptxas otherwise rebuilds it
+        // from the shared-memory base every pulse: ~10 instructions)
+        asm volatile("" : "+r"(line_addr));
+        // carrier phase increment since the segment base [rad], both pixels at once
+        const f32x2 j2 = bcast2(jf);
+        const f32x2 t = fma2(fma2(S.c3, j2, S.c2), j2, S.c1);
+        const f32x2 qr = mul2(t, j2);
+        const f32x2 ang = add2(qr, S.ang0);
+        const f32x2 g = fma2(qr, bcast2(Gr), S.f0m); // sample coordinate - floor(base) - 1/2
+        const f32x2 m = add2(g, bcast2(MAGIC32));    // nearest integer of g == floor(coordinate)
+        const f32x2 f = sub2(g, add2(m, bcast2(-MAGIC32))); // centred fraction in [-1/2, 1/2]
+        jf += 1.0f;
+        float m0, m1, ang0, ang1;
+        unpack2(m, m0, m1);
+        unpack2(ang, ang0, ang1);
+        const unsigned jj0 = (unsigned) (iw0 + __float_as_int(m0));
+        const unsigned jj1 = (unsigned) (iw1 + __float_as_int(m1));
+        jjmax = max(jjmax, max(jj0, jj1));
+        const unsigned j0 = min(jj0, jmax), j1 = min(jj1, jmax);
+        float cs0, sn0, cs1, sn1;
+        if (EDGE) {
+            // outside the pixel's aperture the rotation is zero: nothing accumulates
+            cs0 = sn0 = cs1 = sn1 = 0.f;
+            if (krel0 + (unsigned) kk < (unsigned) S.kspan[0]) sincos_fast(ang0, sn0, cs0);
+            if (krel1 + (unsigned) kk < (unsigned) S.kspan[1]) sincos_fast(ang1, sn1, cs1);
+        } else {
+            sincos_fast(ang0, sn0, cs0);
+            sincos_fast(ang1, sn1, cs1);
+        }
+        f32x2 w[K];
+        Weights<K, D>::eval(f, w, 0u);
+        float w0[K], w1[K];
+#pragma unroll
+        for (int i = 0; i < K; ++i) unpack2(w[i], w0[i], w1[i]);
+        f32x2 a0 = 0ull, a1 = 0ull; // (re, im) of the interpolated sample, pixel 0 / 1
+        if (j1 == j0 + 1) {
+            // shared register window: K+1 samples (+1 when the start is odd)
+            const unsigned base = j0 & ~1u;
+            constexpr int NV = (K + 3) / 2; // 16-byte loads covering K+2 samples
+            f32x2 sm[2 * NV];
+            const uint32_t src = line_addr + base * (uint32_t) sizeof(float2);
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const float4 v4 = lds128(src + 16u * i);
+                sm[2 * i] = pack2(v4.x, v4.y);
+                sm[2 * i + 1] = pack2(v4.z, v4.w);
+            }
+            if (j0 & 1u) {
+#pragma unroll
+                for (int i = 0; i < K; ++i) {
+                    a0 = fma2(bcast2(w0[i]), sm[i + 1], a0);
+                    a1 = fma2(bcast2(w1[i]), sm[i + 2], a1);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < K; ++i) {
+                    a0 = fma2(bcast2(w0[i]), sm[i], a0);
+                    a1 = fma2(bcast2(w1[i]), sm[i + 1], a1);
+                }
+            }
+        } else {
+            // general spacing: independent windows
+            const uint32_t s0 = line_addr + j0 * (uint32_t) sizeof(float2);
+            const uint32_t s1 = line_addr + j1 * (uint32_t) sizeof(float2);
+#pragma unroll
+            for (int i = 0; i < K; ++i) {
+                a0 = fma2(bcast2(w0[i]), lds64(s0 + 8u * i), a0);
+                a1 = fma2(bcast2(w1[i]), lds64(s1 + 8u * i), a1);
+            }
+        }
+        // rotate by the carrier phase and accumulate (zero rotation outside the aperture)
+        S.accp[0] = fma2(bcast2(cs0), a0, S.accp[0]);
+        S.accq[0] = fma2(bcast2(sn0), a0, S.accq[0]);
+        S.accp[1] = fma2(bcast2(cs1), a1, S.accp[1]);
+        S.accq[1] = fma2(bcast2(sn1), a1, S.accq[1]);
+        line_addr += row_bytes;
+    }
 }
 
 template<int K, int D, int UNROLL>
@@ -314,38 +447,43 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, FastParams P,
         }
         hdr->kb = INT_MAX;
         hdr->ke = INT_MIN;
+        hdr->ks_max = INT_MIN;
+        hdr->ke_min = INT_MAX;
         hdr->bad = 0;
         fence_mbar_init();
     }
     __syncthreads();
 
     // ---- prologue: pixel records, CTA pulse range, corner positions ----------------
-    PixState st[PX];
+    // Threads past the grid edge shadow the nearest in-grid pixel (same aperture, nothing
+    // written back), so they never force the aperture test on the rest of the CTA.
+    PairState S;
     long long gidx[PX];
     const int lrow = tid / (TILE_RG / PX);
     const int lcol = (tid % (TILE_RG / PX)) * PX;
     {
         const int last_row = min(TILE_AZ, P.out_lines - line0) - 1;
         const int last_col = min(TILE_RG, P.out_width - col0) - 1;
-        int kmin = INT_MAX, kmax = INT_MIN;
+        int kmin = INT_MAX, kmax = INT_MIN, ksmax = INT_MIN, kemin = INT_MAX;
         bool bad = false;
 #pragma unroll
         for (int p = 0; p < PX; ++p) {
             const int jj = line0 + lrow, ii = col0 + lcol + p;
-            const bool in_grid = (jj < P.out_lines) && (ii < P.out_width);
             const int jc = min(jj, P.out_lines - 1), ic = min(ii, P.out_width - 1);
             gidx[p] = (long long) jc * P.out_width + ic;
             const PixelRec r = pix[gidx[p]];
             if (r.kstart < 0) bad = true;
-            const int ks = in_grid ? max(r.kstart, P.k_begin) : 0;
-            const int ke_p = in_grid ? min(r.kstop, P.k_end) : 0;
-            st[p].kstart = ks;
-            st[p].kspan = max(ke_p - ks, 0);
-            st[p].accp = st[p].accq = 0ull;
+            const int ks = max(r.kstart, P.k_begin);
+            const int ke_p = min(r.kstop, P.k_end);
+            S.kstart[p] = ks;
+            S.kspan[p] = max(ke_p - ks, 0);
+            S.accp[p] = S.accq[p] = 0ull;
             if (ke_p > ks) {
                 kmin = min(kmin, ks);
                 kmax = max(kmax, ke_p);
             }
+            ksmax = max(ksmax, ks);
+            kemin = min(kemin, ke_p);
             // the four corner pixels of the (grid-clipped) tile publish their position
             const int lc = lcol + p;
             const bool top = lrow == 0, bot = lrow == last_row;
@@ -363,16 +501,21 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, FastParams P,
         for (int o = 16; o > 0; o >>= 1) {
             kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
             kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+            ksmax = max(ksmax, __shfl_xor_sync(0xffffffffu, ksmax, o));
+            kemin = min(kemin, __shfl_xor_sync(0xffffffffu, kemin, o));
         }
         const bool anybad = __any_sync(0xffffffffu, bad);
         if (lane == 0) {
             if (kmin != INT_MAX) atomicMin(&hdr->kb, kmin);
             if (kmax != INT_MIN) atomicMax(&hdr->ke, kmax);
+            atomicMax(&hdr->ks_max, ksmax);
+            atomicMin(&hdr->ke_min, kemin);
             if (anybad) hdr->bad = 1;
         }
     }
     __syncthreads();
     const int kb = hdr->kb, ke = hdr->ke;
+    const int ks_max = hdr->ks_max, ke_min = hdr->ke_min;
     if (hdr->bad) {
         if (tid == 0) tile_generic[blockIdx.x] = 1;
         return;
@@ -411,7 +554,7 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, FastParams P,
         __syncwarp();
     };
     if (warp == 0) {
-        for (int n = 0; n < NSTAGE - 1 && n < ntiles; ++n) produce(n);
+        for (int n = 0; n < PREFETCH && n < ntiles; ++n) produce(n);
     }
 
     // Per-thread shared-memory slots: FP64 running sums (2 per pixel) and the exact carrier
@@ -435,19 +578,19 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, FastParams P,
     const uint32_t stage_addr0 = smem_u32(stage0);
     const uint32_t row_bytes = (uint32_t) P.W * (uint32_t) sizeof(float2);
     const unsigned jmax = (unsigned) (P.W - (K + 3));
-    const float TWO_PI_F = 6.28318530717958647692f;
     const double TWO_PI_D = 6.283185307179586476925;
     const float Gr = (float) (P.G / TWO_PI_D); // samples per radian of carrier phase
     float jf = 0.f;                             // pulse index within the segment
 
     for (int n = 0; n < ntiles; ++n) {
-        if (n + NSTAGE - 1 < ntiles && warp == (I3B_ROTATE_PRODUCER ? (n + NSTAGE - 1) % NWARPS_ROT : 0))
-            produce(n + NSTAGE - 1);
+        if (n + PREFETCH < ntiles && warp == (I3B_ROTATE_PRODUCER ? (n + PREFETCH) % NWARPS_ROT : 0))
+            produce(n + PREFETCH);
 
         if ((n % (SEG / TK)) == 0) {
             // ---- new geometry segment: one exact FP64 evaluation per pixel, cubic through
             // the four surrounding boundaries, everything inside the segment is FP32 ----
             const int b = kb + n * TK;
+            float c1[PX], c2[PX], c3[PX], a0[PX], f0[PX];
 #pragma unroll
             for (int p = 0; p < PX; ++p) {
                 const PixelRec q = pix[gidx[p]];
@@ -460,15 +603,20 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, FastParams P,
                 const double d1 = y2 - y1, d2 = (y2 - y1) - (y1 - y0);
                 const double d3 = ((y3 - y2) - (y2 - y1)) - d2;
                 // p(tau) - y1 = tau (d1 - d2/2 - d3/6) + tau^2 d2/2 + tau^3 d3/6, tau = j / SEG
-                st[p].c1 = (float) (TWO_PI_D * (d1 - 0.5 * d2 - d3 * (1.0 / 6.0)) * (1.0 / SEG));
-                st[p].c2 = (float) (TWO_PI_D * (0.5 * d2) * (1.0 / (SEG * SEG)));
-                st[p].c3 = (float) (TWO_PI_D * (d3 * (1.0 / 6.0)) * (1.0 / ((double) SEG * SEG * SEG)));
-                st[p].ang0 = (float) (TWO_PI_D * (y1 - rint(y1)));
+                c1[p] = (float) (TWO_PI_D * (d1 - 0.5 * d2 - d3 * (1.0 / 6.0)) * (1.0 / SEG));
+                c2[p] = (float) (TWO_PI_D * (0.5 * d2) * (1.0 / (SEG * SEG)));
+                c3[p] = (float) (TWO_PI_D * (d3 * (1.0 / 6.0)) * (1.0 / ((double) SEG * SEG * SEG)));
+                a0[p] = (float) (TWO_PI_D * (y1 - rint(y1)));
                 const double uh = fma(y1, P.G, SHIFT - P.U0);
                 const double ufl = floor(uh);
-                st[p].f0m = (float) (uh - ufl) - 0.5f;
-                st[p].i0rel = (int) ufl + LOWOFF - MAGIC32_BITS; // window origin added per tile
+                f0[p] = (float) (uh - ufl) - 0.5f;
+                S.i0rel[p] = (int) ufl + LOWOFF - MAGIC32_BITS; // window origin added per tile
             }
+            S.c1 = pack2(c1[0], c1[1]);
+            S.c2 = pack2(c2[0], c2[1]);
+            S.c3 = pack2(c3[0], c3[1]);
+            S.ang0 = pack2(a0[0], a0[1]);
+            S.f0m = pack2(f0[0], f0[1]);
             jf = 0.f;
         }
 
@@ -476,94 +624,25 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, FastParams P,
         mbar_wait(&hdr->full[s], (n / NSTAGE) & 1);
         const uint32_t lines_addr = stage_addr0 + (uint32_t) s * (uint32_t) sbytes;
         const int wlo = hdr->winlo[s];
+        const int kt = kb + n * TK;
         // k - kstart for the first pulse of the tile, per pixel
-        const unsigned krel0 = (unsigned) (kb + n * TK - st[0].kstart);
-        const unsigned krel1 = (unsigned) (kb + n * TK - st[1].kstart);
+        const unsigned krel0 = (unsigned) (kt - S.kstart[0]);
+        const unsigned krel1 = (unsigned) (kt - S.kstart[1]);
+        if (I3B_EDGE_SPLIT && kt >= ks_max && kt + TK <= ke_min)
+            tile_body<K, D, false>(S, jf, jjmax, lines_addr, row_bytes, wlo, jmax, Gr, krel0, krel1);
+        else
+            tile_body<K, D, true>(S, jf, jjmax, lines_addr, row_bytes, wlo, jmax, Gr, krel0, krel1);
 
-#pragma unroll UNROLL
-        for (int kk = 0; kk < TK; ++kk) {
-            float f[PX], cs[PX], sn[PX];
-            unsigned j0[PX];
-#pragma unroll
-            for (int p = 0; p < PX; ++p) {
-                const PixState& q = st[p];
-                const float t = fmaf(fmaf(q.c3, jf, q.c2), jf, q.c1);
-                const float qr = t * jf;            // carrier phase increment since the base [rad]
-                const float ang = qr + q.ang0;
-                const float g = fmaf(qr, Gr, q.f0m); // sample coordinate - floor(base) - 1/2
-                const float m = g + MAGIC32;         // nearest integer of g == floor(coordinate)
-                f[p] = g - (m - MAGIC32);            // centred fraction in [-1/2, 1/2]
-                const unsigned jj = (unsigned) (q.i0rel + __float_as_int(m) - wlo);
-                jjmax = max(jjmax, jj);
-                j0[p] = min(jj, jmax);
-                // outside the pixel's aperture the rotation is zero: nothing accumulates
-                const bool inside = (p == 0 ? krel0 : krel1) + (unsigned) kk < (unsigned) q.kspan;
-                cs[p] = 0.f;
-                sn[p] = 0.f;
-                if (inside) {
-                    cs[p] = __cosf(ang);
-                    sn[p] = __sinf(ang);
-                }
-            }
-            jf += 1.0f;
-            const uint32_t line_addr = lines_addr + (uint32_t) kk * row_bytes;
-            f32x2 w[K];
-            Weights<K, D>::eval(pack2(f[0], f[1]), w, 0u);
-            float w0[K], w1[K];
-#pragma unroll
-            for (int m = 0; m < K; ++m) unpack2(w[m], w0[m], w1[m]);
-            f32x2 a0 = 0ull, a1 = 0ull; // (re, im) of the interpolated sample, pixel 0 / 1
-            if (j0[1] == j0[0] + 1) {
-                // shared register window: K+1 samples (+1 when the start is odd)
-                const unsigned base = j0[0] & ~1u;
-                constexpr int NV = (K + 3) / 2; // 16-byte loads covering K+2 samples
-                f32x2 sm[2 * NV];
-                const uint32_t src = line_addr + base * (uint32_t) sizeof(float2);
-#pragma unroll
-                for (int i = 0; i < NV; ++i) {
-                    const float4 v4 = lds128(src + 16u * i);
-                    sm[2 * i] = pack2(v4.x, v4.y);
-                    sm[2 * i + 1] = pack2(v4.z, v4.w);
-                }
-                if (j0[0] & 1u) {
-#pragma unroll
-                    for (int m = 0; m < K; ++m) {
-                        a0 = fma2(bcast2(w0[m]), sm[m + 1], a0);
-                        a1 = fma2(bcast2(w1[m]), sm[m + 2], a1);
-                    }
-                } else {
-#pragma unroll
-                    for (int m = 0; m < K; ++m) {
-                        a0 = fma2(bcast2(w0[m]), sm[m], a0);
-                        a1 = fma2(bcast2(w1[m]), sm[m + 1], a1);
-                    }
-                }
-            } else {
-                // general spacing: independent windows
-                const uint32_t s0 = line_addr + j0[0] * (uint32_t) sizeof(float2);
-                const uint32_t s1 = line_addr + j0[1] * (uint32_t) sizeof(float2);
-#pragma unroll
-                for (int m = 0; m < K; ++m) {
-                    a0 = fma2(bcast2(w0[m]), lds64(s0 + 8u * m), a0);
-                    a1 = fma2(bcast2(w1[m]), lds64(s1 + 8u * m), a1);
-                }
-            }
-            // rotate by the carrier phase and accumulate (zero rotation outside the aperture)
-            st[0].accp = fma2(bcast2(cs[0]), a0, st[0].accp);
-            st[0].accq = fma2(bcast2(sn[0]), a0, st[0].accq);
-            st[1].accp = fma2(bcast2(cs[1]), a1, st[1].accp);
-            st[1].accq = fma2(bcast2(sn[1]), a1, st[1].accq);
-        }
         // pulse tile done: fold FP32 partials into FP64, release the stage.
         // sum s*e^{j phi} = (P.x - Q.y) + j (P.y + Q.x)
 #pragma unroll
         for (int p = 0; p < PX; ++p) {
             float px_, py_, qx_, qy_;
-            unpack2(st[p].accp, px_, py_);
-            unpack2(st[p].accq, qx_, qy_);
+            unpack2(S.accp[p], px_, py_);
+            unpack2(S.accq[p], qx_, qy_);
             accd[2 * p] += (double) (px_ - qy_);
             accd[2 * p + 1] += (double) (py_ + qx_);
-            st[p].accp = st[p].accq = 0ull;
+            S.accp[p] = S.accq[p] = 0ull;
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&hdr->empty[s]);
