@@ -234,6 +234,9 @@ typedef struct {
     int64_t h2d_bytes, d2h_bytes;
     int32_t pulse_first, pulse_last; /* [first,last) pulses actually used   */
     int32_t n_devices;
+    int32_t fast_variant;     /* fast path: >= 0 build-time specialised kernel
+                                 (baked coefficient table), -1 the general
+                                 constant-bank kernel                       */
 } I3B_Stats;
 
 /* Device microbenchmarks used as roofline denominators (bench harness).    */
@@ -245,6 +248,27 @@ typedef struct {
     int32_t sm_count;
     int32_t _pad;
 } I3B_Peaks;
+
+/* Per-tap polynomial form of the interpolation kernel used by the fast
+ * accumulation kernel (host-side fit, no device needed): for tap m of K and
+ * the centred fractional sample offset f in [-1/2, 1/2),
+ *   w_m(f)     = E_m(f^2) + f*O_m(f^2),      m < ceil(K/2)
+ *   w_{K-1-m}  = E_m(f^2) - f*O_m(f^2)
+ * even[m][i] multiplies f^(2i), odd[m][i] multiplies f^(2i+1).  max_err is the
+ * largest |polynomial - kernel(x)| over the taps (kernel evaluated exactly as
+ * Kernel<float>::operator(), core/Kernels.icc); `supported` is 0 when the fast
+ * kernel cannot take this kernel (reason in i3b_last_error()).             */
+#define I3B_FIT_MAX_TAP_PAIRS 17
+#define I3B_FIT_MAX_COEF 4
+typedef struct {
+    int32_t taps, degree;
+    int32_t supported;
+    int32_t imm_variant; /* >= 0: index of the build-time specialised kernel
+                            whose baked coefficients equal this fit         */
+    double max_err;
+    float even[I3B_FIT_MAX_TAP_PAIRS][I3B_FIT_MAX_COEF];
+    float odd[I3B_FIT_MAX_TAP_PAIRS][I3B_FIT_MAX_COEF];
+} I3B_TapPolyFit;
 
 /* ---- entry points -------------------------------------------------------- */
 
@@ -267,6 +291,8 @@ const char* i3b_last_error(void);
 const char* i3b_version(void);
 int i3b_device_count(void);
 int i3b_measure_peaks(int device, I3B_Peaks* peaks);
+/* Host-only diagnostic: the polynomial fit the fast kernel would use.      */
+int i3b_fit_tap_polynomials(const I3B_Kernel* kernel, I3B_TapPolyFit* fit);
 
 #ifdef __cplusplus
 }

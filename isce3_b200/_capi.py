@@ -185,6 +185,7 @@ class Stats(C.Structure):
         ("pulse_first", C.c_int32),
         ("pulse_last", C.c_int32),
         ("n_devices", C.c_int32),
+        ("fast_variant", C.c_int32),
     ]
 
     def as_dict(self):
@@ -207,6 +208,22 @@ class Peaks(C.Structure):
 
 # entry points include/isce3_b200_backproject.h declares; tests check that the
 # built library exports every one of them.
+FIT_MAX_TAP_PAIRS = 17
+FIT_MAX_COEF = 4
+
+
+class TapPolyFit(C.Structure):
+    _fields_ = [
+        ("taps", C.c_int32),
+        ("degree", C.c_int32),
+        ("supported", C.c_int32),
+        ("imm_variant", C.c_int32),
+        ("max_err", C.c_double),
+        ("even", (C.c_float * FIT_MAX_COEF) * FIT_MAX_TAP_PAIRS),
+        ("odd", (C.c_float * FIT_MAX_COEF) * FIT_MAX_TAP_PAIRS),
+    ]
+
+
 EXPORTED_SYMBOLS = (
     "i3b_backproject",
     "i3b_plan_create",
@@ -218,6 +235,7 @@ EXPORTED_SYMBOLS = (
     "i3b_version",
     "i3b_device_count",
     "i3b_measure_peaks",
+    "i3b_fit_tap_polynomials",
 )
 
 LIB_NAME = "libisce3_b200_backproject.so"
@@ -256,6 +274,8 @@ def load_library() -> C.CDLL:
     lib.i3b_device_count.restype = C.c_int
     lib.i3b_measure_peaks.argtypes = [C.c_int, C.POINTER(Peaks)]
     lib.i3b_measure_peaks.restype = C.c_int
+    lib.i3b_fit_tap_polynomials.argtypes = [C.POINTER(Kernel), C.POINTER(TapPolyFit)]
+    lib.i3b_fit_tap_polynomials.restype = C.c_int
     _lib = lib
     return lib
 

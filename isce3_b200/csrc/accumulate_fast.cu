@@ -33,6 +33,7 @@
 #include "geometry.cuh"
 #include "kernels.cuh"
 #include "launch.h"
+#include "tap_poly_imm.h" // generated: baked coefficient tables of the specialised kernels
 
 #include <climits>
 
@@ -149,6 +150,7 @@ struct FastParams {
     double G;       // samples per cycle: 1 / (fc * dtau)
     double U0;      // swst / dtau
     double fc;
+    int zero;       // always 0 (opaque to the compiler, see Weights::load_top)
 };
 
 constexpr double MAGIC = 805306368.0; // 1.5 * 2^29: ulp 2^-23, integer part in mantissa bits 23..
@@ -231,26 +233,77 @@ __device__ __forceinline__ double2 lds_d2(uint32_t addr)
     return v;
 }
 
-template<int K, int D>
+// Coefficient sources for the weight polynomials.  CoefBank reads the fitted rows from the
+// constant bank (any kernel; costs ~22 LDC per pulse at K = 9 because FFMA2 has no
+// constant-bank operand form).  CoefImm<V> reads a build-time table (tap_poly_imm.h): after
+// unrolling every coefficient is an FFMA2 immediate -- no loads at all.  The launcher picks
+// CoefImm<V> only when the run-time fit of the caller's kernel equals table V.
+struct CoefBank {
+    static constexpr bool kImm = false;
+    __device__ static __forceinline__ float e(int m, int i) { return c_poly[m].e[i]; }
+    __device__ static __forceinline__ float o(int m, int i) { return c_poly[m].o[i]; }
+};
+template<int V>
+struct CoefImm {
+    static constexpr bool kImm = true;
+    __device__ static __forceinline__ constexpr float e(int m, int i) { return imm::Table<V>::even(m, i); }
+    __device__ static __forceinline__ constexpr float o(int m, int i) { return imm::Table<V>::odd(m, i); }
+};
+
+#ifndef I3B_HOIST_TOP
+#define I3B_HOIST_TOP 1
+#endif
+template<int K, int D, class Coef>
 struct Weights {
+    static constexpr int NE = D / 2 + 1;       // even coefficients  f^0, f^2, ...
+    static constexpr int NO = (D + 1) / 2;     // odd coefficients   f^1, f^3, ...
+    static constexpr bool kHoist = Coef::kImm && I3B_HOIST_TOP;
+    // Leading coefficients.  An FFMA2 takes ONE immediate, so the first Horner step
+    // (c_top * h + c_next) needs c_top in a register; left to itself ptxas re-creates these
+    // registers every pulse with FMA-pipe moves (IMAD.MOV / HFMA2, 2 issue cycles each next
+    // to FFMA2).  Loaded once per pulse tile and made opaque instead.
+    struct Top {
+        float e[(K + 1) / 2];
+        float o[K / 2 > 0 ? K / 2 : 1];
+    };
+    // `zero` is a kernel parameter that is always 0: adding it to the bit pattern keeps ptxas
+    // from constant-propagating the value back into per-pulse immediate moves.
+    __device__ static __forceinline__ void load_top(Top& t, int zero)
+    {
+        if (kHoist) {
+#pragma unroll
+            for (int m = 0; m < (K + 1) / 2; ++m)
+                t.e[m] = __int_as_float(__float_as_int(Coef::e(m, NE - 1)) + zero);
+#pragma unroll
+            for (int m = 0; m < K / 2; ++m)
+                t.o[m] = __int_as_float(__float_as_int(Coef::o(m, NO - 1)) + zero);
+        }
+    }
     // Tap weights of TWO pixels at once: f = (f_pixel0, f_pixel1) in [-0.5, 0.5);
     // w[m] = (w_m(f0), w_m(f1)).  Coefficients enter as scalar-broadcast operands.
-    __device__ static __forceinline__ void eval(f32x2 f, f32x2 (&w)[K], uint32_t poly_addr)
+    __device__ static __forceinline__ void eval(f32x2 f, f32x2 (&w)[K], const Top& top)
     {
-        constexpr int NE = D / 2 + 1;       // even coefficients  f^0, f^2, ...
-        constexpr int NO = (D + 1) / 2;     // odd coefficients   f^1, f^3, ...
         const f32x2 h = mul2(f, f);
         const f32x2 nf = mul2(f, bcast2(-1.0f));
 #pragma unroll
         for (int m = 0; m < K / 2; ++m) {
-#if I3B_POLY_SMEM
-            // broadcast LDS.128: one wavefront each, no constant-cache (LDC.64) round trips
-            const float4 ce = lds128(poly_addr + 32u * m), co = lds128(poly_addr + 32u * m + 16u);
-#else
-            const float4 ce = *reinterpret_cast<const float4*>(c_poly[m].e);
-            const float4 co = *reinterpret_cast<const float4*>(c_poly[m].o);
-#endif
-            const float cev[4] = {ce.x, ce.y, ce.z, ce.w}, cov[4] = {co.x, co.y, co.z, co.w};
+            float cev[4], cov[4];
+            if (Coef::kImm) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    cev[i] = Coef::e(m, i);
+                    cov[i] = Coef::o(m, i);
+                }
+                if (kHoist) {
+                    cev[NE - 1] = top.e[m];
+                    cov[NO - 1] = top.o[m];
+                }
+            } else {
+                const float4 ce = *reinterpret_cast<const float4*>(c_poly[m].e);
+                const float4 co = *reinterpret_cast<const float4*>(c_poly[m].o);
+                cev[0] = ce.x; cev[1] = ce.y; cev[2] = ce.z; cev[3] = ce.w;
+                cov[0] = co.x; cov[1] = co.y; cov[2] = co.z; cov[3] = co.w;
+            }
             f32x2 e = bcast2(cev[NE - 1]);
 #pragma unroll
             for (int i = NE - 2; i >= 0; --i) e = fma2(e, h, bcast2(cev[i]));
@@ -262,12 +315,15 @@ struct Weights {
         }
         if (K & 1) {
             constexpr int m = K / 2;
-#if I3B_POLY_SMEM
-            const float4 ce = lds128(poly_addr + 32u * m);
-#else
-            const float4 ce = *reinterpret_cast<const float4*>(c_poly[m].e);
-#endif
-            const float cev[4] = {ce.x, ce.y, ce.z, ce.w};
+            float cev[4];
+            if (Coef::kImm) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) cev[i] = Coef::e(m, i);
+                if (kHoist) cev[NE - 1] = top.e[m];
+            } else {
+                const float4 ce = *reinterpret_cast<const float4*>(c_poly[m].e);
+                cev[0] = ce.x; cev[1] = ce.y; cev[2] = ce.z; cev[3] = ce.w;
+            }
             f32x2 e = bcast2(cev[NE - 1]);
 #pragma unroll
             for (int i = NE - 2; i >= 0; --i) e = fma2(e, h, bcast2(cev[i]));
@@ -294,7 +350,7 @@ __device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b)
 // coordinate arithmetic of both pixels is one FFMA2 / FADD2 / FMUL2 each.
 struct PairState {
     f32x2 ang0;        // 2*pi*(carrier phase in cycles at the segment base, reduced to [-1/2, 1/2])
-    f32x2 f0m;         // frac(sample coordinate at the segment base) - 1/2
+    f32x2 f0m;         // frac(sample coordinate at the segment base) - 1/2 - Gr * ang0
     f32x2 c1, c2, c3;  // carrier phase increment over the segment: ((c3 j + c2) j + c1) j  [rad]
     int i0rel[PX];     // window start at the base minus the magic bias (window origin added per tile)
     f32x2 accp[PX], accq[PX]; // FP32 partial sums of the pulse tile: sum cos*(re,im), sum sin*(re,im)
@@ -331,13 +387,43 @@ __device__ __forceinline__ void sincos_fast(float x, float& sn, float& cs)
 #endif
 }
 
+// MAC of both pixels over the shared register window + carrier rotation into the tile sums.
+// OFF = 0: window starts on an even sample, 1: odd.
+template<int K, int OFF, int NS>
+__device__ __forceinline__ void mac_rotate(PairState& S, const f32x2 (&w)[K], const f32x2 (&sm)[NS],
+                                           float cs0, float sn0, float cs1, float sn1)
+{
+    f32x2 a0 = 0ull, a1 = 0ull; // (re, im) of the interpolated sample, pixel 0 / 1
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+        float w0, w1;
+        unpack2(w[i], w0, w1);
+        a0 = fma2(bcast2(w0), sm[i + OFF], a0);
+        a1 = fma2(bcast2(w1), sm[i + OFF + 1], a1);
+    }
+    // rotate by the carrier phase and accumulate (zero rotation outside the aperture)
+    S.accp[0] = fma2(bcast2(cs0), a0, S.accp[0]);
+    S.accq[0] = fma2(bcast2(sn0), a0, S.accq[0]);
+    S.accp[1] = fma2(bcast2(cs1), a1, S.accp[1]);
+    S.accq[1] = fma2(bcast2(sn1), a1, S.accq[1]);
+}
+
 // One staged pulse tile (TK pulses) for the thread's pixel pair.  EDGE = false: every pixel
 // of the CTA integrates every pulse of the tile (no aperture test in the loop).
-template<int K, int D, bool EDGE>
+//
+// Issue-cost model measured on B200 (scripts/ubench/pipes2.cu, 4 warps per scheduler): FFMA2 /
+// FADD2 / FMUL2 2.1 cycles, scalar FFMA / IMAD / FMUL 2.0 (no cheaper than the packed form),
+// FADD 1.4, LOP3 / IADD3 / VIMNMX 0.6-0.9, MOV / LDS ~0.2 (issue in the FFMA2 shadow), MUFU 8
+// XU cycles (asynchronous).  So the loop is written to be FFMA2-only on the FMA pipe.
+template<int K, int D, class Coef, bool EDGE>
 __device__ __forceinline__ void tile_body(PairState& S, float& jf, unsigned& jjmax,
                                           uint32_t lines_addr, uint32_t row_bytes, int wlo,
-                                          unsigned jmax, float Gr, unsigned krel0, unsigned krel1)
+                                          unsigned jmax, float Gr, unsigned krel0, unsigned krel1,
+                                          int zero)
 {
+    typedef Weights<K, D, Coef> WT;
+    typename WT::Top top;
+    WT::load_top(top, zero);
     const int iw0 = S.i0rel[0] - wlo, iw1 = S.i0rel[1] - wlo;
     uint32_t line_addr = lines_addr;
 #pragma unroll 1
@@ -345,13 +431,11 @@ __device__ __forceinline__ void tile_body(PairState& S, float& jf, unsigned& jjm
         // keep the staged line address a loop-carried register (ptxas otherwise rebuilds it
         // from the shared-memory base every pulse: ~10 instructions)
         asm volatile("" : "+r"(line_addr));
-        // carrier phase increment since the segment base [rad], both pixels at once
+        // carrier phase [rad] (reduced at the segment base) of both pixels at once
         const f32x2 j2 = bcast2(jf);
-        const f32x2 t = fma2(fma2(S.c3, j2, S.c2), j2, S.c1);
-        const f32x2 qr = mul2(t, j2);
-        const f32x2 ang = add2(qr, S.ang0);
-        const f32x2 g = fma2(qr, bcast2(Gr), S.f0m); // sample coordinate - floor(base) - 1/2
-        const f32x2 m = add2(g, bcast2(MAGIC32));    // nearest integer of g == floor(coordinate)
+        const f32x2 ang = fma2(fma2(fma2(S.c3, j2, S.c2), j2, S.c1), j2, S.ang0);
+        const f32x2 g = fma2(ang, bcast2(Gr), S.f0m); // sample coordinate - floor(base) - 1/2
+        const f32x2 m = add2(g, bcast2(MAGIC32));     // nearest integer of g == floor(coordinate)
         const f32x2 f = sub2(g, add2(m, bcast2(-MAGIC32))); // centred fraction in [-1/2, 1/2]
         jf += 1.0f;
         float m0, m1, ang0, ang1;
@@ -372,56 +456,44 @@ __device__ __forceinline__ void tile_body(PairState& S, float& jf, unsigned& jjm
             sincos_fast(ang1, sn1, cs1);
         }
         f32x2 w[K];
-        Weights<K, D>::eval(f, w, 0u);
-        float w0[K], w1[K];
-#pragma unroll
-        for (int i = 0; i < K; ++i) unpack2(w[i], w0[i], w1[i]);
-        f32x2 a0 = 0ull, a1 = 0ull; // (re, im) of the interpolated sample, pixel 0 / 1
         if (j1 == j0 + 1) {
-            // shared register window: K+1 samples (+1 when the start is odd)
-            const unsigned base = j0 & ~1u;
+            // shared register window: K+1 samples (+1 when the start is odd); the loads are
+            // issued BEFORE the weight polynomials so their latency hides behind them
             constexpr int NV = (K + 3) / 2; // 16-byte loads covering K+2 samples
             f32x2 sm[2 * NV];
-            const uint32_t src = line_addr + base * (uint32_t) sizeof(float2);
+            const uint32_t src = line_addr + ((j0 >> 1) << 4);
 #pragma unroll
             for (int i = 0; i < NV; ++i) {
                 const float4 v4 = lds128(src + 16u * i);
                 sm[2 * i] = pack2(v4.x, v4.y);
                 sm[2 * i + 1] = pack2(v4.z, v4.w);
             }
-            if (j0 & 1u) {
-#pragma unroll
-                for (int i = 0; i < K; ++i) {
-                    a0 = fma2(bcast2(w0[i]), sm[i + 1], a0);
-                    a1 = fma2(bcast2(w1[i]), sm[i + 2], a1);
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < K; ++i) {
-                    a0 = fma2(bcast2(w0[i]), sm[i], a0);
-                    a1 = fma2(bcast2(w1[i]), sm[i + 1], a1);
-                }
-            }
+            WT::eval(f, w, top);
+            if (j0 & 1u) mac_rotate<K, 1>(S, w, sm, cs0, sn0, cs1, sn1);
+            else mac_rotate<K, 0>(S, w, sm, cs0, sn0, cs1, sn1);
         } else {
             // general spacing: independent windows
+            WT::eval(f, w, top);
             const uint32_t s0 = line_addr + j0 * (uint32_t) sizeof(float2);
             const uint32_t s1 = line_addr + j1 * (uint32_t) sizeof(float2);
+            f32x2 a0 = 0ull, a1 = 0ull;
 #pragma unroll
             for (int i = 0; i < K; ++i) {
-                a0 = fma2(bcast2(w0[i]), lds64(s0 + 8u * i), a0);
-                a1 = fma2(bcast2(w1[i]), lds64(s1 + 8u * i), a1);
+                float w0, w1;
+                unpack2(w[i], w0, w1);
+                a0 = fma2(bcast2(w0), lds64(s0 + 8u * i), a0);
+                a1 = fma2(bcast2(w1), lds64(s1 + 8u * i), a1);
             }
+            S.accp[0] = fma2(bcast2(cs0), a0, S.accp[0]);
+            S.accq[0] = fma2(bcast2(sn0), a0, S.accq[0]);
+            S.accp[1] = fma2(bcast2(cs1), a1, S.accp[1]);
+            S.accq[1] = fma2(bcast2(sn1), a1, S.accq[1]);
         }
-        // rotate by the carrier phase and accumulate (zero rotation outside the aperture)
-        S.accp[0] = fma2(bcast2(cs0), a0, S.accp[0]);
-        S.accq[0] = fma2(bcast2(sn0), a0, S.accq[0]);
-        S.accp[1] = fma2(bcast2(cs1), a1, S.accp[1]);
-        S.accq[1] = fma2(bcast2(sn1), a1, S.accq[1]);
         line_addr += row_bytes;
     }
 }
 
-template<int K, int D, int UNROLL>
+template<int K, int D, class Coef>
 __global__ void __launch_bounds__(NTHREADS, 2)
 accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, FastParams P,
                        const PixelRec* __restrict__ pix, const PulseRec* __restrict__ pulse,
@@ -616,7 +688,8 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, FastParams P,
             S.c2 = pack2(c2[0], c2[1]);
             S.c3 = pack2(c3[0], c3[1]);
             S.ang0 = pack2(a0[0], a0[1]);
-            S.f0m = pack2(f0[0], f0[1]);
+            // the loop evaluates coordinate = f0m + Gr * (ang0 + increment)
+            S.f0m = pack2(f0[0] - Gr * a0[0], f0[1] - Gr * a0[1]);
             jf = 0.f;
         }
 
@@ -629,9 +702,9 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, FastParams P,
         const unsigned krel0 = (unsigned) (kt - S.kstart[0]);
         const unsigned krel1 = (unsigned) (kt - S.kstart[1]);
         if (I3B_EDGE_SPLIT && kt >= ks_max && kt + TK <= ke_min)
-            tile_body<K, D, false>(S, jf, jjmax, lines_addr, row_bytes, wlo, jmax, Gr, krel0, krel1);
+            tile_body<K, D, Coef, false>(S, jf, jjmax, lines_addr, row_bytes, wlo, jmax, Gr, krel0, krel1, P.zero);
         else
-            tile_body<K, D, true>(S, jf, jjmax, lines_addr, row_bytes, wlo, jmax, Gr, krel0, krel1);
+            tile_body<K, D, Coef, true>(S, jf, jjmax, lines_addr, row_bytes, wlo, jmax, Gr, krel0, krel1, P.zero);
 
         // pulse tile done: fold FP32 partials into FP64, release the stage.
         // sum s*e^{j phi} = (P.x - Q.y) + j (P.y + Q.x)
@@ -759,22 +832,71 @@ constexpr double FIT_TOL = 3e-5;
 
 static bool taps_supported(int K) { return K == 8 || K == 9 || K == 16 || K == 32; }
 
-bool fast_supported(const DevKernel& hk, char* why, size_t why_len)
+// Index of the baked table (tap_poly_imm.h) equal to this fit, or -1.  "Equal" = every
+// coefficient within 2e-7 absolute: the two fits then give weights that differ by less than
+// FP32 rounding of the Horner evaluation itself, whichever machine produced the table.
+static int match_imm_table(const FitResult& R)
 {
-    if (!taps_supported(hk.taps)) {
-        snprintf(why, why_len, "tap count %d has no fast instantiation (8, 9, 16, 32)", hk.taps);
-        return false;
+    for (int v = 0; v < imm::kNumTables; ++v) {
+        const imm::Desc& d = imm::kDesc[v];
+        if (d.taps != R.K || d.degree != R.D) continue;
+        double worst = 0;
+        for (int m = 0; m < (R.K + 1) / 2; ++m)
+            for (int i = 0; i < MAX_COEF / 2; ++i) {
+                worst = std::max(worst, (double) std::fabs(d.even[m * 4 + i] - R.even[m][i]));
+                worst = std::max(worst, (double) std::fabs(d.odd[m * 4 + i] - R.odd[m][i]));
+            }
+        if (worst <= 2e-7) return v;
+    }
+    return -1;
+}
+
+// I3B_FAST_NO_IMM=1 (test / tuning knob, read per call): always use the general kernel
+static bool imm_enabled()
+{
+    const char* e = std::getenv("I3B_FAST_NO_IMM");
+    return !(e && std::atoi(e) != 0);
+}
+
+int fast_fit(const DevKernel& hk, I3B_TapPolyFit* fit, char* why, size_t why_len)
+{
+    std::memset(fit, 0, sizeof *fit);
+    fit->imm_variant = -1;
+    fit->taps = hk.taps;
+    if (why_len) why[0] = 0;
+    if (hk.taps < 1 || hk.taps > MAX_TAPS) {
+        snprintf(why, why_len, "tap count %d outside [1, %d]", hk.taps, MAX_TAPS);
+        return 0;
     }
     if (hk.kind == I3B_KERNEL_BARTLETT || hk.kind == I3B_KERNEL_LINEAR) {
         snprintf(why, why_len, "piecewise-linear kernel is not polynomial per tap");
-        return false;
+        return 0;
     }
     const FitResult R = fit_kernel(hk, FIT_TOL);
+    fit->degree = R.D;
+    fit->max_err = R.max_err;
+    for (int m = 0; m < (R.K + 1) / 2; ++m)
+        for (int i = 0; i < MAX_COEF / 2; ++i) {
+            fit->even[m][i] = R.even[m][i];
+            fit->odd[m][i] = R.odd[m][i];
+        }
+    fit->imm_variant = imm_enabled() ? match_imm_table(R) : -1;
+    if (!taps_supported(hk.taps)) {
+        snprintf(why, why_len, "tap count %d has no fast instantiation (8, 9, 16, 32)", hk.taps);
+        return 0;
+    }
     if (!R.ok) {
         snprintf(why, why_len, "per-tap polynomial fit residual %.2e > %.1e", R.max_err, FIT_TOL);
-        return false;
+        return 0;
     }
-    return true;
+    fit->supported = 1;
+    return 1;
+}
+
+bool fast_supported(const DevKernel& hk, char* why, size_t why_len)
+{
+    I3B_TapPolyFit fit;
+    return fast_fit(hk, &fit, why, why_len) != 0;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -795,17 +917,36 @@ static EncodeTiledFn get_encode_fn()
     return fn;
 }
 
-template<int K, int D, int UNROLL>
-static int launch_inst(const CUtensorMap& map, const FastParams& FP, const PixelRec* pix,
-                       const PulseRec* pulse, double2* acc, unsigned char* tile_generic,
-                       DevStatus* status, size_t smem, cudaStream_t s)
+struct LaunchArgs {
+    const CUtensorMap* map;
+    const FastParams* FP;
+    const PixelRec* pix;
+    const PulseRec* pulse;
+    double2* acc;
+    unsigned char* tile_generic;
+    DevStatus* status;
+    size_t smem;
+    cudaStream_t s;
+};
+
+template<int K, int D, class Coef>
+static int launch_inst(const LaunchArgs& L)
 {
-    auto kern = accumulate_fast_kernel<K, D, UNROLL>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    auto kern = accumulate_fast_kernel<K, D, Coef>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) L.smem);
     if (e != cudaSuccess) return (int) e;
-    const unsigned grid = (unsigned) (FP.tiles_rg * FP.tiles_az);
-    kern<<<grid, NTHREADS, smem, s>>>(map, FP, pix, pulse, acc, tile_generic, status);
+    const unsigned grid = (unsigned) (L.FP->tiles_rg * L.FP->tiles_az);
+    kern<<<grid, NTHREADS, L.smem, L.s>>>(*L.map, *L.FP, L.pix, L.pulse, L.acc, L.tile_generic, L.status);
     return (int) cudaGetLastError();
+}
+
+// build-time specialised instantiations, one per table of tap_poly_imm.h
+template<int V>
+static int launch_imm(int v, const LaunchArgs& L)
+{
+    if (v == V) return launch_inst<imm::Table<V>::taps, imm::Table<V>::degree, CoefImm<V>>(L);
+    if constexpr (V + 1 < imm::kNumTables) return launch_imm<V + 1>(v, L);
+    return -1;
 }
 
 // Returns 0 on success, >0 a cudaError_t, -1 if the configuration is unsupported
@@ -820,8 +961,9 @@ int launch_accumulate_fast(const AccumParams& P, const DevKernel& hk, const Pixe
     const double out_in_spacing_ratio = P.spacing_ratio;
     // the magic-number splits need |fc*tau| and |u| below 2^28
     if (P.fc * (P.swst + (P.nr + 64) * P.dtau) > 2.6e8 || P.nr > (1 << 27)) return -1;
+    if (!taps_supported(hk.taps)) return -1;
     const FitResult R = fit_kernel(hk, FIT_TOL);
-    if (!R.ok || !taps_supported(hk.taps)) return -1;
+    if (!R.ok) return -1;
     const int K = hk.taps;
     int W = (int) std::ceil(TILE_RG * std::fabs(out_in_spacing_ratio) * 1.002) + K + 16;
 #ifdef I3B_EXTRA_W
@@ -841,10 +983,6 @@ int launch_accumulate_fast(const AccumParams& P, const DevKernel& hk, const Pixe
                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return -1;
 
-    cudaError_t e;
-    e = cudaMemcpyToSymbolAsync(c_poly, R.rows, sizeof(R.rows), 0, cudaMemcpyHostToDevice, s);
-    if (e != cudaSuccess) return (int) e;
-
     FastParams FP;
     FP.npix = P.npix;
     FP.out_lines = P.out_lines;
@@ -861,18 +999,22 @@ int launch_accumulate_fast(const AccumParams& P, const DevKernel& hk, const Pixe
     FP.G = 1.0 / (P.fc * P.dtau);
     FP.U0 = P.swst / P.dtau;
     FP.fc = P.fc;
+    FP.zero = 0;
     const size_t smem = HEADER_BYTES + NSTAGE * stage_bytes(W) + (size_t) NTHREADS * 6 * PX * sizeof(double);
-    static const int unroll2 = [] {
-        const char* e = std::getenv("I3B_FAST_UNROLL"); // tuning knob (default 1)
-        return e && std::atoi(e) == 2;
-    }();
+    const LaunchArgs L{&map, &FP, pix, pulse, acc, tile_generic, status, smem, s};
+
+    const int v = imm_enabled() ? match_imm_table(R) : -1;
+    if (v >= 0) {
+        const int r = launch_imm<0>(v, L);
+        if (r >= 0) return r;
+    }
+    cudaError_t e = cudaMemcpyToSymbolAsync(c_poly, R.rows, sizeof(R.rows), 0, cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) return (int) e;
     switch (K) {
-    case 8: return launch_inst<8, 7, 1>(map, FP, pix, pulse, acc, tile_generic, status, smem, s);
-    case 9:
-        return unroll2 ? launch_inst<9, 6, 2>(map, FP, pix, pulse, acc, tile_generic, status, smem, s)
-                       : launch_inst<9, 6, 1>(map, FP, pix, pulse, acc, tile_generic, status, smem, s);
-    case 16: return launch_inst<16, 7, 1>(map, FP, pix, pulse, acc, tile_generic, status, smem, s);
-    case 32: return launch_inst<32, 7, 1>(map, FP, pix, pulse, acc, tile_generic, status, smem, s);
+    case 8: return launch_inst<8, 7, CoefBank>(L);
+    case 9: return launch_inst<9, 6, CoefBank>(L);
+    case 16: return launch_inst<16, 7, CoefBank>(L);
+    case 32: return launch_inst<32, 7, CoefBank>(L);
     default: return -1;
     }
 }

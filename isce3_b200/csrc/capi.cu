@@ -205,6 +205,7 @@ struct Shard {
     AccumParams ap;
     DevKernel host_kernel;
     bool use_fast = false;
+    int fast_variant = -1;
     I3B_Stats stats;
     int status_code = 0;
     std::string error;
@@ -313,7 +314,9 @@ static void shard_setup(const HostScene& hs, Shard& sh)
     A.tiles_rg = (A.out_width + A.tile_rg - 1) / A.tile_rg;
     sh.host_kernel = make_kernel(a.kernel, a.kernel.data);
     char why[160] = "";
-    sh.use_fast = !(a.flags & I3B_FLAG_FORCE_GENERIC) && fast_supported(sh.host_kernel, why, sizeof why);
+    I3B_TapPolyFit fit;
+    sh.use_fast = !(a.flags & I3B_FLAG_FORCE_GENERIC) && fast_fit(sh.host_kernel, &fit, why, sizeof why);
+    sh.fast_variant = sh.use_fast ? fit.imm_variant : -1;
     std::memset(&sh.stats, 0, sizeof sh.stats);
     sh.stats.taps = A.kernel.taps;
 }
@@ -467,6 +470,7 @@ static void shard_run(const HostScene& hs, Shard& sh, bool resident_only)
     sh.stats.ms_accumulate = elapsed(ea0, ea1);
     sh.stats.ms_h2d = ms_h2d;
     sh.stats.used_fast_kernel = sh.use_fast ? 1 : 0;
+    sh.stats.fast_variant = sh.use_fast ? sh.fast_variant : -1;
     if (st.window_overflow && sh.use_fast) {
         // the staged range window was too small for some gather: redo with the generic kernel
         sh.use_fast = false;
@@ -612,6 +616,7 @@ static void merge_stats(I3B_Plan& plan, double ms_total)
         t.total_launches += s.total_launches;
         t.used_fast_kernel &= s.used_fast_kernel;
         t.taps = s.taps;
+        t.fast_variant = s.fast_variant;
         t.h2d_bytes += s.h2d_bytes;
         t.d2h_bytes += s.d2h_bytes;
         if (s.pulse_last > s.pulse_first) {
@@ -746,6 +751,18 @@ int i3b_measure_peaks(int device, I3B_Peaks* peaks)
         if (!peaks) throw ApiError(I3B_EXC_INVALID_ARGUMENT, "null peaks pointer");
         const int rc = measure_peaks(device, peaks);
         if (rc != 0) CK((cudaError_t) rc);
+        return 0;
+    });
+}
+
+int i3b_fit_tap_polynomials(const I3B_Kernel* kernel, I3B_TapPolyFit* fit)
+{
+    return guarded([&]() {
+        if (!kernel || !fit) throw ApiError(I3B_EXC_INVALID_ARGUMENT, "null argument");
+        const DevKernel hk = make_kernel(*kernel, kernel->data);
+        char why[160] = "";
+        fast_fit(hk, fit, why, sizeof why);
+        g_last_error = why;
         return 0;
     });
 }

@@ -52,6 +52,7 @@ int launch_accumulate_fast(const AccumParams& P, const DevKernel& host_kernel,
                            const PixelRec* pix, const PulseRec* pulse, const float2* rc,
                            double2* acc, unsigned char* tile_generic, DevStatus* status,
                            cudaStream_t s);
+int fast_fit(const DevKernel& host_kernel, I3B_TapPolyFit* fit, char* why, size_t why_len);
 int fast_tiles(int out_lines, int out_width);
 void fast_tile_shape(int* tile_az, int* tile_rg);
 // The pulse table holds records for pulses [-kPulsePadLo, n_pulses + kPulsePadHi): the entries

@@ -22,4 +22,4 @@ with BackprojectPlan(*sc.backproject_args()) as plan:
     pp = st["pixel_pulses"]
     best = min(ms)
     taps = st["taps"]
-    print(f"{tag}: kernel {best:.1f} ms  {pp / best * 1e3:.4g} pp/s  frac(73.9T) {(34 + 10 * taps) * pp / best * 1e3 / 73.9e12:.3f} fast={st['used_fast_kernel']} all={['%.1f' % m for m in ms]}", flush=True)
+    print(f"{tag}: variant={st["fast_variant"]} kernel {best:.1f} ms  {pp / best * 1e3:.4g} pp/s  frac(73.9T) {(34 + 10 * taps) * pp / best * 1e3 / 73.9e12:.3f} fast={st['used_fast_kernel']} all={['%.1f' % m for m in ms]}", flush=True)
