@@ -357,7 +357,14 @@ struct PairState {
     int kstart[PX], kspan[PX]; // aperture: kstart <= k < kstart + kspan
 };
 
-constexpr int SEG = 32; // pulses per geometry segment
+#ifndef I3B_SEG
+#define I3B_SEG 64
+#endif
+#ifndef I3B_KK_UNROLL
+#define I3B_KK_UNROLL 2
+#endif
+constexpr int SEG = I3B_SEG; // pulses per geometry segment
+constexpr int KK_UNROLL = I3B_KK_UNROLL;
 static_assert(SEG % TK == 0, "a geometry segment is a whole number of staged pulse tiles");
 constexpr float MAGIC32 = 12582912.0f;         // 1.5 * 2^23: float -> nearest integer by addition
 constexpr int MAGIC32_BITS = 0x4B400000;
@@ -426,7 +433,7 @@ __device__ __forceinline__ void tile_body(PairState& S, float& jf, unsigned& jjm
     WT::load_top(top, zero);
     const int iw0 = S.i0rel[0] - wlo, iw1 = S.i0rel[1] - wlo;
     uint32_t line_addr = lines_addr;
-#pragma unroll 1
+#pragma unroll KK_UNROLL
     for (int kk = 0; kk < TK; ++kk) {
         // keep the staged line address a loop-carried register (ptxas otherwise rebuilds it
         // from the shared-memory base every pulse: ~10 instructions)

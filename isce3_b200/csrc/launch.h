@@ -58,8 +58,8 @@ void fast_tile_shape(int* tile_az, int* tile_rg);
 // The pulse table holds records for pulses [-kPulsePadLo, n_pulses + kPulsePadHi): the entries
 // outside the input grid are orbit EXTRAPOLATIONS (smooth continuation), used by the fast
 // kernel's segment-boundary evaluations and by staged tiles that run over the ends.
-constexpr int kPulsePadLo = 64;
-constexpr int kPulsePadHi = 160;
+constexpr int kPulsePadLo = 128;
+constexpr int kPulsePadHi = 288;
 
 int measure_peaks(int device, I3B_Peaks* out);
 

@@ -78,6 +78,22 @@ def test_c2_like_tsx_noise_full_aperture(oracle):
     check(gpu, run_cpu(oracle, sc), sc)
 
 
+def test_specialised_and_general_fast_kernels_agree(oracle, monkeypatch):
+    """The workflow kernel (Knab(9, 1/1.2) on a 2048-point table, focus.py:794-803) runs the
+    build-time specialised kernel (coefficients as FFMA2 immediates); I3B_FAST_NO_IMM=1 forces
+    the general constant-bank kernel.  Same polynomials, same arithmetic: same image."""
+    sc = synth.make_scene("c2", pulses=4096, bins=1024, out_lines=20, out_samples=300, n_targets=1)
+    imm = run_gpu(sc)
+    assert imm[3]["used_fast_kernel"] == 1 and imm[3]["fast_variant"] == 0
+    monkeypatch.setenv("I3B_FAST_NO_IMM", "1")
+    bank = run_gpu(sc)
+    assert bank[3]["used_fast_kernel"] == 1 and bank[3]["fast_variant"] == -1
+    assert np.linalg.norm(imm[1] - bank[1]) <= 2e-6 * np.linalg.norm(bank[1])
+    cpu = run_cpu(oracle, sc)
+    check(imm, cpu, sc)
+    check(bank, cpu, sc)
+
+
 def test_irf_metrics_match_oracle(oracle):
     """Point-target IRF of the GPU image vs the oracle image: peak location within 0.01
     sample, PSLR and ISLR within 0.05 dB, in both axes (nov = 32 on a 32-pixel chip)."""
