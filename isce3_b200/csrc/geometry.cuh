@@ -46,48 +46,41 @@ __device__ inline int linspace_search(double first, double spacing, int size, do
     return (int) ((val - first) / spacing + 1);
 }
 
-// Cubic Hermite through 4 state vectors (positions and velocities).
+// Cubic Hermite through 4 state vectors (positions and velocities):
+// interpolateOrbitHermite, InterpolateOrbit.icc:15-109.  The state vectors are uniformly
+// spaced (Orbit holds a Linspace), so with u_k = (t - t_k)/dt the reference's basis
+//   h_i = prod_{j!=i} (t - t_j)/(t_i - t_j),  sum_i = sum_{j!=i} 1/(t_i - t_j), ...
+// reduces to products of the u_k with small rational constants: the same polynomial, no
+// divisions (the reference form costs 36 FP64 divisions per call, and the call sits inside
+// the geo2rdr root finder).  Differs from the literal form by rounding only (~1e-15 rel.).
 __device__ inline void orbit_hermite(const DevOrbit& o, double t, D3* pos, D3* vel)
 {
     int idx = linspace_search(o.t0, o.dt, o.n, t) - 2;
     idx = min(max(idx, 0), o.n - 4);
-    double tt[4], d[4], h[4], hdot[4], gsum[4];
+    const double inv_dt = 1.0 / o.dt;
+    double u[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        tt[i] = o.t0 + (idx + i) * o.dt;
-        d[i] = t - tt[i];
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        double s = 0., hh = 1., hd = 0.;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (j == i) continue;
-            const double inv = 1. / (tt[i] - tt[j]);
-            s += inv;
-            hh *= d[j] / (tt[i] - tt[j]);
-            double prod = inv;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (k == i || k == j) continue;
-                prod *= d[k] / (tt[i] - tt[k]);
-            }
-            hd += prod;
-        }
-        gsum[i] = s;
-        h[i] = hh;
-        hdot[i] = hd;
-    }
+    for (int i = 0; i < 4; ++i) u[i] = (t - (o.t0 + (idx + i) * o.dt)) * inv_dt;
+    // c_i = 1 / prod_{j != i} (i - j),  S_i = sum_{j != i} 1 / (i - j)
+    const double c[4] = {-1.0 / 6.0, 0.5, -0.5, 1.0 / 6.0};
+    const double S[4] = {-11.0 / 6.0, -0.5, 0.5, 11.0 / 6.0};
+    const double u01 = u[0] * u[1], u23 = u[2] * u[3];
+    // products of the other three u's, and sums of their pairwise products
+    const double P3[4] = {u[1] * u23, u[0] * u23, u01 * u[3], u01 * u[2]};
+    const double E2[4] = {fma(u[1], u[2] + u[3], u23), fma(u[0], u[2] + u[3], u23),
+                          fma(u[3], u[0] + u[1], u01), fma(u[2], u[0] + u[1], u01)};
     D3 p = {0, 0, 0}, v = {0, 0, 0};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const double f0 = 1. - 2. * gsum[i] * d[i];
-        const double f1 = d[i];
-        const double g1 = h[i] + 2. * hdot[i] * d[i];
-        const double g0 = 2. * (f0 * hdot[i] - gsum[i] * h[i]);
+        const double h = c[i] * P3[i];
+        const double hd_dt = c[i] * E2[i];          // hdot_i * dt
+        const double f0 = fma(-2.0 * S[i], u[i], 1.0);
+        const double f1 = u[i] * o.dt;
+        const double g1 = fma(2.0 * hd_dt, u[i], h);
+        const double g0 = 2.0 * inv_dt * (f0 * hd_dt - S[i] * h);
         const D3 P = ld3(o.pos, idx + i), V = ld3(o.vel, idx + i);
-        p = p + (h[i] * h[i]) * (P * f0 + V * f1);
-        v = v + h[i] * (P * g0 + V * g1);
+        p = p + (h * h) * (P * f0 + V * f1);
+        v = v + h * (P * g0 + V * g1);
     }
     *pos = p;
     *vel = v;
@@ -177,6 +170,24 @@ __device__ inline D3 xyz_to_llh(D3 p3)
     llh.x = atan2(p3.y, p3.x);
     llh.z = ((k + kE2 - 1.) * sqrt(d * d + p3.z * p3.z)) / k;
     return llh;
+}
+
+// Height above the ellipsoid only (same closed form; skips the two atan2 of the angles).
+__device__ inline double xyz_to_height(D3 p3)
+{
+    const double e4 = kE2 * kE2, a2 = kA * kA;
+    const double rho2 = p3.x * p3.x + p3.y * p3.y;
+    const double p = rho2 / a2;
+    const double q = (1. - kE2) * (p3.z * p3.z) / a2;
+    const double r = (p + q - e4) / 6.;
+    const double s = (e4 * p * q) / (4. * r * r * r);
+    const double t = cbrt(1. + s + sqrt(s * (2. + s)));
+    const double u = r * (1. + t + (1. / t));
+    const double rv = sqrt(u * u + e4 * q);
+    const double w = (kE2 * (u + rv - q)) / (2. * rv);
+    const double k = sqrt(u + rv + w * w) - w;
+    const double d = (k * sqrt(rho2)) / (k + kE2);
+    return ((k + kE2 - 1.) * sqrt(d * d + p3.z * p3.z)) / k;
 }
 
 __device__ inline D3 n_vector(double lon, double lat)
@@ -444,22 +455,50 @@ __device__ inline int rdr2geo_bracket(double aztime, double slant_range, double 
         sincos(look, &sl, &cl);
         return center + (radius * sl) * horizontal + (radius * cl) * down;
     };
-    auto dh = [&](double look) {
-        const D3 llh = xyz_to_llh(get_xyz(look));
-        return llh.z - dem_interp_lonlat(dem, llh.x, llh.y);
-    };
     const double tol_look = prm.tol_height / radius;
     double look = 0.0;
+    if (!dem.have_raster) {
+        // Constant-height DEM: the height error is monotonic in the look angle, so the root in
+        // [look_min, look_max] is unique.  Bracket it tightly around the spherical-Earth
+        // solution first (same root finder, same tolerance: the result is the root to within
+        // tol_look either way); the full interval of the reference is the fallback.
+        auto dh_flat = [&](double look_) { return xyz_to_height(get_xyz(look_)) - dem.ref_height; };
+        const double sinpsi = radar.z / norm(radar);   // geocentric latitude of the platform
+        const double re = kA * sqrt((1.0 - kE2) / (1.0 - kE2 * (1.0 - sinpsi * sinpsi))) + dem.ref_height;
+        const double cguess = (re * re - dot(center, center) - radius * radius) /
+                              (2.0 * radius * dot(radar, down));
+        if (fabs(cguess) < 1.0) {
+            const double g = acos(cguess);
+            const double lo = fmax(g - 0.02, prm.look_min), hi = fmin(g + 0.02, prm.look_max);
+            if (lo < hi && brent(lo, hi, dh_flat, tol_look, &look) == I3B_SUCCESS) {
+                *xyz = get_xyz(look);
+                return I3B_SUCCESS;
+            }
+        }
+        const int err = brent(prm.look_min, prm.look_max, dh_flat, tol_look, &look);
+        if (err != I3B_SUCCESS) return err;
+        *xyz = get_xyz(look);
+        return I3B_SUCCESS;
+    }
+    auto dh = [&](double look_) {
+        const D3 llh = xyz_to_llh(get_xyz(look_));
+        return llh.z - dem_interp_lonlat(dem, llh.x, llh.y);
+    };
     const int err = brent(prm.look_min, prm.look_max, dh, tol_look, &look);
     if (err != I3B_SUCCESS) return err;
     *xyz = get_xyz(look);
     return I3B_SUCCESS;
 }
 
+// `t_guess`: where the root is expected (the output line's time when both geometries share
+// the orbit).  The Doppler error is first bracketed in a few seconds around it -- same root
+// finder and tolerance as the reference, so the answer is the root to within tol_aztime
+// either way -- and the reference's full interval is the fallback (also taken when the
+// guess is NaN).
 __device__ inline int geo2rdr_bracket(D3 x, const DevOrbit& orbit, const DevLUT2d& dop,
                                       double wavelength, int side,
                                       const I3B_Geo2RdrBracketParams& prm, double* aztime,
-                                      double* range)
+                                      double* range, double t_guess = nan(""))
 {
     const double orbit_start = orbit.t0, orbit_end = orbit.t0 + (orbit.n - 1) * orbit.dt;
     double t0, t1;
@@ -475,7 +514,12 @@ __device__ inline int geo2rdr_bracket(D3 x, const DevOrbit& orbit, const DevLUT2
         const double fd = lut2d_eval(dop, t, rnorm);
         return 2.0 / wavelength * dot(v, r) / rnorm - fd;
     };
-    const int err = brent(t0, t1, doppler_error, prm.tol_aztime, aztime);
+    int err = I3B_INVALID_INTERVAL;
+    if (t_guess == t_guess) {
+        const double lo = fmax(t_guess - 4.0, t0), hi = fmin(t_guess + 4.0, t1);
+        if (lo < hi) err = brent(lo, hi, doppler_error, prm.tol_aztime, aztime);
+    }
+    if (err != I3B_SUCCESS) err = brent(t0, t1, doppler_error, prm.tol_aztime, aztime);
     if (err != I3B_SUCCESS) return err;
     orbit_interpolate(orbit, *aztime, BORDER_FILLNAN, &xp, &v);
     r = x - xp;

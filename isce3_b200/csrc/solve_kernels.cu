@@ -74,7 +74,7 @@ target_solve_kernel(SolveParams P, PixelRec* __restrict__ pix, float* __restrict
             const D3 llh = xyz_to_llh(x);
             h = (float) llh.z;
             double tc, rc;
-            st = geo2rdr_bracket(x, P.in_orbit, P.in_doppler, P.wvl, P.in_side, P.g2r, &tc, &rc);
+            st = geo2rdr_bracket(x, P.in_orbit, P.in_doppler, P.wvl, P.in_side, P.g2r, &tc, &rc, t);
             if (st != I3B_SUCCESS) {
                 status->soft_error = I3B_FAILED_TO_CONVERGE;
             } else {
