@@ -14,8 +14,11 @@
  * i3b_last_error() returns the message of the last failure on this thread.
  *
  * All arrays are caller-owned, row-major, host memory (pageable is fine).  The
- * callee owns every device allocation and frees it before returning (one-shot
- * call) or at i3b_plan_destroy() (resident plan).
+ * callee owns every device allocation and returns it before returning (one-shot
+ * call) or at i3b_plan_destroy() (resident plan) -- to the device's stream-ordered
+ * memory pool, which keeps it cached for the next call (a workflow calls
+ * backproject once per output block); i3b_release_device_memory() gives the
+ * cached memory back to the driver, I3B_POOL_KEEP_MB=<n> caps what is kept.
  */
 #ifndef ISCE3_B200_BACKPROJECT_H
 #define ISCE3_B200_BACKPROJECT_H
@@ -291,6 +294,8 @@ const char* i3b_last_error(void);
 const char* i3b_version(void);
 int i3b_device_count(void);
 int i3b_measure_peaks(int device, I3B_Peaks* peaks);
+/* Return device memory cached by earlier calls to the driver (all devices). */
+int i3b_release_device_memory(void);
 /* Host-only diagnostic: the polynomial fit the fast kernel would use.      */
 int i3b_fit_tap_polynomials(const I3B_Kernel* kernel, I3B_TapPolyFit* fit);
 

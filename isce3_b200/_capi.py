@@ -236,6 +236,7 @@ EXPORTED_SYMBOLS = (
     "i3b_device_count",
     "i3b_measure_peaks",
     "i3b_fit_tap_polynomials",
+    "i3b_release_device_memory",
 )
 
 LIB_NAME = "libisce3_b200_backproject.so"
@@ -276,6 +277,7 @@ def load_library() -> C.CDLL:
     lib.i3b_measure_peaks.restype = C.c_int
     lib.i3b_fit_tap_polynomials.argtypes = [C.POINTER(Kernel), C.POINTER(TapPolyFit)]
     lib.i3b_fit_tap_polynomials.restype = C.c_int
+    lib.i3b_release_device_memory.restype = C.c_int
     _lib = lib
     return lib
 

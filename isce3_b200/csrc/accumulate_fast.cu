@@ -394,11 +394,28 @@ __device__ __forceinline__ void sincos_fast(float x, float& sn, float& cs)
 #endif
 }
 
+// Carrier rotation of the interpolated samples into the tile sums.  EDGE tiles skip pulses
+// outside a pixel's aperture altogether (never 0 * sample: staged rows outside the aperture
+// may hold anything, including NaN / Inf or rows whose upload is still in flight).
+template<bool EDGE>
+__device__ __forceinline__ void rotate_accumulate(PairState& S, f32x2 a0, f32x2 a1, float cs0, float sn0,
+                                                  float cs1, float sn1, bool in0, bool in1)
+{
+    if (!EDGE || in0) {
+        S.accp[0] = fma2(bcast2(cs0), a0, S.accp[0]);
+        S.accq[0] = fma2(bcast2(sn0), a0, S.accq[0]);
+    }
+    if (!EDGE || in1) {
+        S.accp[1] = fma2(bcast2(cs1), a1, S.accp[1]);
+        S.accq[1] = fma2(bcast2(sn1), a1, S.accq[1]);
+    }
+}
+
 // MAC of both pixels over the shared register window + carrier rotation into the tile sums.
 // OFF = 0: window starts on an even sample, 1: odd.
-template<int K, int OFF, int NS>
+template<int K, int OFF, bool EDGE, int NS>
 __device__ __forceinline__ void mac_rotate(PairState& S, const f32x2 (&w)[K], const f32x2 (&sm)[NS],
-                                           float cs0, float sn0, float cs1, float sn1)
+                                           float cs0, float sn0, float cs1, float sn1, bool in0, bool in1)
 {
     f32x2 a0 = 0ull, a1 = 0ull; // (re, im) of the interpolated sample, pixel 0 / 1
 #pragma unroll
@@ -408,11 +425,7 @@ __device__ __forceinline__ void mac_rotate(PairState& S, const f32x2 (&w)[K], co
         a0 = fma2(bcast2(w0), sm[i + OFF], a0);
         a1 = fma2(bcast2(w1), sm[i + OFF + 1], a1);
     }
-    // rotate by the carrier phase and accumulate (zero rotation outside the aperture)
-    S.accp[0] = fma2(bcast2(cs0), a0, S.accp[0]);
-    S.accq[0] = fma2(bcast2(sn0), a0, S.accq[0]);
-    S.accp[1] = fma2(bcast2(cs1), a1, S.accp[1]);
-    S.accq[1] = fma2(bcast2(sn1), a1, S.accq[1]);
+    rotate_accumulate<EDGE>(S, a0, a1, cs0, sn0, cs1, sn1, in0, in1);
 }
 
 // One staged pulse tile (TK pulses) for the thread's pixel pair.  EDGE = false: every pixel
@@ -453,15 +466,11 @@ __device__ __forceinline__ void tile_body(PairState& S, float& jf, unsigned& jjm
         jjmax = max(jjmax, max(jj0, jj1));
         const unsigned j0 = min(jj0, jmax), j1 = min(jj1, jmax);
         float cs0, sn0, cs1, sn1;
-        if (EDGE) {
-            // outside the pixel's aperture the rotation is zero: nothing accumulates
-            cs0 = sn0 = cs1 = sn1 = 0.f;
-            if (krel0 + (unsigned) kk < (unsigned) S.kspan[0]) sincos_fast(ang0, sn0, cs0);
-            if (krel1 + (unsigned) kk < (unsigned) S.kspan[1]) sincos_fast(ang1, sn1, cs1);
-        } else {
-            sincos_fast(ang0, sn0, cs0);
-            sincos_fast(ang1, sn1, cs1);
-        }
+        // pulses outside a pixel's aperture (EDGE tiles only) are skipped at the rotation
+        const bool in0 = !EDGE || krel0 + (unsigned) kk < (unsigned) S.kspan[0];
+        const bool in1 = !EDGE || krel1 + (unsigned) kk < (unsigned) S.kspan[1];
+        sincos_fast(ang0, sn0, cs0);
+        sincos_fast(ang1, sn1, cs1);
         f32x2 w[K];
         if (j1 == j0 + 1) {
             // shared register window: K+1 samples (+1 when the start is odd); the loads are
@@ -476,8 +485,8 @@ __device__ __forceinline__ void tile_body(PairState& S, float& jf, unsigned& jjm
                 sm[2 * i + 1] = pack2(v4.z, v4.w);
             }
             WT::eval(f, w, top);
-            if (j0 & 1u) mac_rotate<K, 1>(S, w, sm, cs0, sn0, cs1, sn1);
-            else mac_rotate<K, 0>(S, w, sm, cs0, sn0, cs1, sn1);
+            if (j0 & 1u) mac_rotate<K, 1, EDGE>(S, w, sm, cs0, sn0, cs1, sn1, in0, in1);
+            else mac_rotate<K, 0, EDGE>(S, w, sm, cs0, sn0, cs1, sn1, in0, in1);
         } else {
             // general spacing: independent windows
             WT::eval(f, w, top);
@@ -491,10 +500,7 @@ __device__ __forceinline__ void tile_body(PairState& S, float& jf, unsigned& jjm
                 a0 = fma2(bcast2(w0), lds64(s0 + 8u * i), a0);
                 a1 = fma2(bcast2(w1), lds64(s1 + 8u * i), a1);
             }
-            S.accp[0] = fma2(bcast2(cs0), a0, S.accp[0]);
-            S.accq[0] = fma2(bcast2(sn0), a0, S.accq[0]);
-            S.accp[1] = fma2(bcast2(cs1), a1, S.accp[1]);
-            S.accq[1] = fma2(bcast2(sn1), a1, S.accq[1]);
+            rotate_accumulate<EDGE>(S, a0, a1, cs0, sn0, cs1, sn1, in0, in1);
         }
         line_addr += row_bytes;
     }

@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <thread>
@@ -45,29 +46,51 @@ struct ApiError : std::runtime_error {
 static thread_local std::string g_last_error;
 static thread_local I3B_Stats g_last_stats;
 
+// Device buffers come from the device's stream-ordered memory pool (cudaMallocAsync) with
+// the release threshold raised, so a second call of the same size allocates without talking
+// to the driver: a workflow calls backproject once per output block (focus.py:1988-2007), and
+// in a process that has enabled peer access (NCCL, multi-GPU) every plain cudaMalloc/cudaFree
+// has to map/unmap the allocation on all peers -- measured 850 ms per call for this path's
+// ~6 GB at 2 GPUs.  i3b_release_device_memory() hands the cached memory back.
+static void configure_pool(int device)
+{
+    static std::mutex mtx;
+    static std::vector<int> done;
+    std::lock_guard<std::mutex> lock(mtx);
+    if (std::find(done.begin(), done.end(), device) != done.end()) return;
+    cudaMemPool_t pool;
+    CK(cudaDeviceGetDefaultMemPool(&pool, device));
+    unsigned long long threshold = ~0ull;
+    if (const char* e = std::getenv("I3B_POOL_KEEP_MB")) threshold = std::strtoull(e, nullptr, 10) << 20;
+    CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+    done.push_back(device);
+}
+
 template<typename T>
 struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
+    cudaStream_t stream = nullptr; // allocation / release are ordered on this stream
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
     ~DevBuf() { release(); }
     void release()
     {
-        if (p) cudaFree(p);
+        if (p) cudaFreeAsync(p, stream);
         p = nullptr;
         n = 0;
     }
-    void alloc(size_t count)
+    void alloc(size_t count, cudaStream_t s)
     {
         release();
         n = count;
-        if (count) CK(cudaMalloc(&p, count * sizeof(T)));
+        stream = s;
+        if (count) CK(cudaMallocAsync(&p, count * sizeof(T), s));
     }
     void upload(const T* src, size_t count, cudaStream_t s)
     {
-        alloc(count);
+        alloc(count, s);
         if (count) CK(cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, s));
     }
 };
@@ -189,7 +212,21 @@ static DevKernel make_kernel(const I3B_Kernel& k, const float* data)
 struct Shard {
     int device = 0;
     int line0 = 0, nlines = 0;
-    cudaStream_t compute = nullptr, copy = nullptr;
+    // declared before the buffers: members are destroyed in reverse order, so the streams
+    // outlive the stream-ordered frees of the buffers below
+    struct Streams {
+        cudaStream_t compute = nullptr, copy = nullptr;
+        ~Streams()
+        {
+            if (compute) {
+                cudaStreamSynchronize(compute); // drains the cudaFreeAsync of the buffers
+                cudaStreamDestroy(compute);
+            }
+            if (copy) cudaStreamDestroy(copy);
+        }
+    } streams;
+    cudaStream_t& compute = streams.compute;
+    cudaStream_t& copy = streams.copy;
     DevBuf<double> out_pos, out_vel, in_pos, in_vel, out_dop, in_dop, pv;
     DevBuf<float> dem, kdata, height;
     DevBuf<PulseRec> pulse;
@@ -212,9 +249,8 @@ struct Shard {
 
     ~Shard()
     {
+        // the buffers and streams are released right after this body, on this thread
         if (compute || copy) cudaSetDevice(device);
-        if (compute) cudaStreamDestroy(compute);
-        if (copy) cudaStreamDestroy(copy);
     }
 };
 
@@ -239,6 +275,7 @@ static void shard_setup(const HostScene& hs, Shard& sh)
     if (prop.major < 10)
         throw ApiError(I3B_EXC_NO_DEVICE,
                        std::string("device ") + prop.name + " is not sm_100-class; isce3_b200 has no fallback path");
+    configure_pool(sh.device);
     CK(cudaStreamCreateWithFlags(&sh.compute, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&sh.copy, cudaStreamNonBlocking));
     cudaStream_t s = sh.compute;
@@ -288,15 +325,15 @@ static void shard_setup(const HostScene& hs, Shard& sh)
 
     const size_t npix = (size_t) sh.nlines * og.grid.width;
     const int n_pulses = (int) ig.grid.length;
-    sh.pulse.alloc((size_t) n_pulses + kPulsePadLo + kPulsePadHi);
+    sh.pulse.alloc((size_t) n_pulses + kPulsePadLo + kPulsePadHi, s);
     CK(cudaMemsetAsync(sh.pulse.p, 0, sh.pulse.n * sizeof(PulseRec), s));
-    sh.pv.alloc((size_t) 6 * std::max(n_pulses, 1));
-    sh.status.alloc(1);
-    sh.pix.alloc(npix);
-    sh.acc.alloc(npix);
-    sh.out.alloc(npix);
-    sh.height.alloc(npix);
-    sh.tile_mask.alloc((size_t) std::max(fast_tiles(sh.nlines, (int) og.grid.width), 1));
+    sh.pv.alloc((size_t) 6 * std::max(n_pulses, 1), s);
+    sh.status.alloc(1, s);
+    sh.pix.alloc(npix, s);
+    sh.acc.alloc(npix, s);
+    sh.out.alloc(npix, s);
+    sh.height.alloc(npix, s);
+    sh.tile_mask.alloc((size_t) std::max(fast_tiles(sh.nlines, (int) og.grid.width), 1), s);
 
     AccumParams& A = sh.ap;
     std::memset(&A, 0, sizeof A);
@@ -419,10 +456,15 @@ static void shard_run(const HostScene& hs, Shard& sh, bool resident_only)
                 sh.rc_pitch = (nr + 1) & ~1; // 16-byte line pitch (TMA global stride rule)
                 sh.rc_k0 = kfirst;
                 sh.rc_rows = klast - kfirst;
-                sh.rc.alloc((size_t) sh.rc_rows * sh.rc_pitch);
+                sh.rc.alloc((size_t) sh.rc_rows * sh.rc_pitch, s);
                 sh.rc_dev = sh.rc.p;
-                if (sh.rc_pitch != nr)
-                    CK(cudaMemsetAsync(sh.rc.p, 0, sh.rc.n * sizeof(float2), sh.copy));
+                // the copy stream fills what the compute stream allocated
+                Event allocated;
+                allocated.record(s);
+                CK(cudaStreamWaitEvent(sh.copy, allocated.e, 0));
+                // pool memory is recycled: clear it, so that rows a pulse tile stages ahead of
+                // the landed slab (and the pad column) never hold stale bit patterns
+                CK(cudaMemsetAsync(sh.rc.p, 0, sh.rc.n * sizeof(float2), sh.copy));
             }
         }
         ea0.record(s);
@@ -767,6 +809,19 @@ int i3b_measure_peaks(int device, I3B_Peaks* peaks)
         if (!peaks) throw ApiError(I3B_EXC_INVALID_ARGUMENT, "null peaks pointer");
         const int rc = measure_peaks(device, peaks);
         if (rc != 0) CK((cudaError_t) rc);
+        return 0;
+    });
+}
+
+int i3b_release_device_memory(void)
+{
+    return guarded([&]() {
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+        for (int d = 0; d < n; ++d) {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, d) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+        }
         return 0;
     });
 }

@@ -223,6 +223,11 @@ class BackprojectPlan:
             pass
 
 
+def release_device_memory() -> None:
+    """Hand the device memory cached by earlier calls back to the driver."""
+    _capi.load_library().i3b_release_device_memory()
+
+
 def measure_peaks(device=0) -> dict:
     pk = _capi.Peaks()
     lib = _capi.load_library()

@@ -197,6 +197,37 @@ def test_clipped_apertures_and_chunking_invariance(oracle):
     assert 0 < pp < 20 * 4 * 3000
 
 
+def test_non_finite_samples_only_poison_the_apertures_that_hold_them(oracle):
+    """A NaN pulse near the start of the aperture of the first output lines: those lines are
+    NaN (they integrate it), later lines -- whose apertures start after it but which share
+    pulse tiles with the first ones on the GPU -- must stay finite, exactly like the CPU."""
+    sc = synth.make_scene("c2", pulses=6144, bins=1024, out_lines=16, out_samples=130, n_targets=1)
+    probe = np.zeros(shape_of(sc), np.complex64)
+    oracle.backproject(probe, *sc.backproject_args())
+    assert np.isfinite(probe).all()
+    # find the first pulse used by line 0 through the oracle's own NaN response
+    lo, hi = 0, sc.rc.shape[0] - 1
+    base = sc.rc.copy()
+    while lo < hi:  # bisection on "line 0 integrates pulse k"
+        mid = (lo + hi) // 2
+        sc.rc = base.copy()
+        sc.rc[:mid + 1] = np.nan
+        o = np.zeros(shape_of(sc), np.complex64)
+        oracle.backproject(o, *sc.backproject_args())
+        if np.isnan(o[0]).any():
+            hi = mid
+        else:
+            lo = mid + 1
+    kstart0 = lo
+    sc.rc = base.copy()
+    sc.rc[kstart0 + 6] = np.nan
+    gpu = run_gpu(sc)
+    cpu = run_cpu(oracle, sc)
+    nan_rows = np.isnan(cpu[1]).all(axis=1)
+    assert nan_rows.any() and not nan_rows.all()
+    check(gpu, cpu)
+
+
 def test_failed_pixels_are_nan_and_flagged(oracle):
     """geo2rdr bracket that excludes part of the image: those pixels are (NaN, NaN), the call
     returns True (FailedToConverge); rdr2geo failure also NaNs the height layer."""
