@@ -353,6 +353,17 @@ def run_ours(args):
         "hbm_peak_gbs": peaks_file.get("hbm_gbs"),
         "measured_peaks": peaks, "traffic": None,
     }
+    # DRAM traffic of the dominant kernel: one ncu capture of this workload, committed under
+    # profiles/ (per launch, like `achieved`); only quoted for the workload it was taken on
+    try:
+        tr = json.loads((ROOT / "profiles" / "r01_traffic.json").read_text())
+        if world == 1 and args.config == "c2" and args.scale == 1.0 and not args.taps:
+            roofline["traffic"] = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+            roofline["traffic_unit"] = "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)"
+            roofline["traffic_source"] = tr["source"]
+            roofline["algorithmic_bytes_per_launch"] = alg_bytes + 32.0 * shape[0] * shape[1]
+    except Exception:
+        pass
 
     cpu = None
     if not args.no_cpu:

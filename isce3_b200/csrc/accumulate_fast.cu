@@ -62,6 +62,10 @@ constexpr int POLY_OFFSET = 256;   // per-tap polynomial rows (copied from const
 #define I3B_PREFETCH_DIST (I3B_NSTAGE - 2)
 #endif
 constexpr int PREFETCH = I3B_PREFETCH_DIST;
+#ifndef I3B_GROUP_RG
+#define I3B_GROUP_RG 2
+#endif
+constexpr int GROUP_RG = I3B_GROUP_RG; // range columns per azimuth-major tile group
 #ifndef I3B_EDGE_SPLIT
 #define I3B_EDGE_SPLIT 1
 #endif
@@ -537,7 +541,21 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, FastParams P,
     const size_t sbytes = stage_bytes(P.W);
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const int tile_i = blockIdx.x % P.tiles_rg, tile_j = blockIdx.x / P.tiles_rg;
+    // Tile order: azimuth-major inside groups of GROUP_RG range columns.  CTAs are started
+    // in blockIdx order, so the ~300 co-resident CTAs are ~150 consecutive azimuth tiles of
+    // the same 2 range columns: they stream the SAME pulse lines a few pulses apart and share
+    // them in L2.  (Range-major order made every wave of CTAs re-read its whole aperture
+    // window from HBM: 598 GB of DRAM reads per C2 frame, ncu r01 v7.)
+    int tile_i, tile_j;
+    {
+        const int per_group = P.tiles_az * GROUP_RG;
+        const int grp = blockIdx.x / per_group;
+        const int rem = blockIdx.x - grp * per_group;
+        const int gcols = min(GROUP_RG, P.tiles_rg - grp * GROUP_RG);
+        tile_j = rem / gcols;
+        tile_i = grp * GROUP_RG + rem - tile_j * gcols;
+    }
+    const int tile_id = tile_j * P.tiles_rg + tile_i; // row-major id (generic-kernel tile mask)
     const int col0 = tile_i * TILE_RG, line0 = tile_j * TILE_AZ;
 
     constexpr int LOWOFF = (K & 1) ? -(K / 2) : 1 - K / 2;
@@ -620,7 +638,7 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, FastParams P,
     const int kb = hdr->kb, ke = hdr->ke;
     const int ks_max = hdr->ks_max, ke_min = hdr->ke_min;
     if (hdr->bad) {
-        if (tid == 0) tile_generic[blockIdx.x] = 1;
+        if (tid == 0) tile_generic[tile_id] = 1;
         return;
     }
     if (kb >= ke) return; // nothing to integrate in this launch
