@@ -15,10 +15,10 @@
  *
  * All arrays are caller-owned, row-major, host memory (pageable is fine).  The
  * callee owns every device allocation and returns it before returning (one-shot
- * call) or at i3b_plan_destroy() (resident plan) -- to the device's stream-ordered
- * memory pool, which keeps it cached for the next call (a workflow calls
- * backproject once per output block); i3b_release_device_memory() gives the
- * cached memory back to the driver, I3B_POOL_KEEP_MB=<n> caps what is kept.
+ * call) or at i3b_plan_destroy() (resident plan) -- to a per-process cache that
+ * keeps it for the next call (a workflow calls backproject once per output
+ * block); i3b_release_device_memory() gives the cached memory back to the
+ * driver, I3B_POOL_KEEP_MB=<n> caps what is kept (0: nothing).
  */
 #ifndef ISCE3_B200_BACKPROJECT_H
 #define ISCE3_B200_BACKPROJECT_H

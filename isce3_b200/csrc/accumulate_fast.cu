@@ -532,7 +532,7 @@ template<int K, int D, class Coef>
 __global__ void __launch_bounds__(NTHREADS, 2)
 accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, FastParams P,
                        const PixelRec* __restrict__ pix, const PulseRec* __restrict__ pulse,
-                       double2* __restrict__ acc, unsigned char* __restrict__ tile_generic,
+                       double2* __restrict__ acc, const TileInfo* __restrict__ tiles,
                        DevStatus* status)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -555,8 +555,14 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, FastParams P,
         tile_j = rem / gcols;
         tile_i = grp * GROUP_RG + rem - tile_j * gcols;
     }
-    const int tile_id = tile_j * P.tiles_rg + tile_i; // row-major id (generic-kernel tile mask)
+    const int tile_id = tile_j * P.tiles_rg + tile_i; // row-major id (target-solve tile table)
     const int col0 = tile_i * TILE_RG, line0 = tile_j * TILE_AZ;
+    {
+        // nothing of this tile in the launch's pulse range (or a failed pixel: generic kernel's
+        // job): leave before touching the pixel records
+        const TileInfo ti = tiles[tile_id];
+        if (ti.bad || ti.kmax <= P.k_begin || ti.kmin >= P.k_end || ti.kmin >= ti.kmax) return;
+    }
 
     constexpr int LOWOFF = (K & 1) ? -(K / 2) : 1 - K / 2;
     constexpr double SHIFT = (K & 1) ? 0.5 : 0.0;
@@ -637,10 +643,7 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, FastParams P,
     __syncthreads();
     const int kb = hdr->kb, ke = hdr->ke;
     const int ks_max = hdr->ks_max, ke_min = hdr->ke_min;
-    if (hdr->bad) {
-        if (tid == 0) tile_generic[tile_id] = 1;
-        return;
-    }
+    if (hdr->bad) return; // (tile table says the same)
     if (kb >= ke) return; // nothing to integrate in this launch
     const int ntiles = (ke - kb + TK - 1) / TK;
 
@@ -972,7 +975,7 @@ struct LaunchArgs {
     const PixelRec* pix;
     const PulseRec* pulse;
     double2* acc;
-    unsigned char* tile_generic;
+    const TileInfo* tiles;
     DevStatus* status;
     size_t smem;
     cudaStream_t s;
@@ -985,7 +988,7 @@ static int launch_inst(const LaunchArgs& L)
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) L.smem);
     if (e != cudaSuccess) return (int) e;
     const unsigned grid = (unsigned) (L.FP->tiles_rg * L.FP->tiles_az);
-    kern<<<grid, NTHREADS, L.smem, L.s>>>(*L.map, *L.FP, L.pix, L.pulse, L.acc, L.tile_generic, L.status);
+    kern<<<grid, NTHREADS, L.smem, L.s>>>(*L.map, *L.FP, L.pix, L.pulse, L.acc, L.tiles, L.status);
     return (int) cudaGetLastError();
 }
 
@@ -999,12 +1002,11 @@ static int launch_imm(int v, const LaunchArgs& L)
 }
 
 // Returns 0 on success, >0 a cudaError_t, -1 if the configuration is unsupported
-// (caller falls back to the generic kernel).  `tile_generic` (one byte per tile, zeroed by
-// the caller) is set for tiles that hold failed pixels; the caller runs the generic kernel
-// on those tiles.
+// (caller falls back to the generic kernel).  Tiles flagged bad in `tiles` (a failed pixel)
+// are skipped; the caller runs the generic kernel on those tiles.
 int launch_accumulate_fast(const AccumParams& P, const DevKernel& hk, const PixelRec* pix,
                            const PulseRec* pulse, const float2* rc, double2* acc,
-                           unsigned char* tile_generic, DevStatus* status, cudaStream_t s)
+                           const TileInfo* tiles, DevStatus* status, cudaStream_t s)
 {
     const int rc_rows = P.rc_rows, n_pulses = P.n_pulses;
     const double out_in_spacing_ratio = P.spacing_ratio;
@@ -1050,7 +1052,7 @@ int launch_accumulate_fast(const AccumParams& P, const DevKernel& hk, const Pixe
     FP.fc = P.fc;
     FP.zero = 0;
     const size_t smem = HEADER_BYTES + NSTAGE * stage_bytes(W) + (size_t) NTHREADS * 6 * PX * sizeof(double);
-    const LaunchArgs L{&map, &FP, pix, pulse, acc, tile_generic, status, smem, s};
+    const LaunchArgs L{&map, &FP, pix, pulse, acc, tiles, status, smem, s};
 
     const int v = imm_enabled() ? match_imm_table(R) : -1;
     if (v >= 0) {

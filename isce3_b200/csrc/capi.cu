@@ -46,51 +46,134 @@ struct ApiError : std::runtime_error {
 static thread_local std::string g_last_error;
 static thread_local I3B_Stats g_last_stats;
 
-// Device buffers come from the device's stream-ordered memory pool (cudaMallocAsync) with
-// the release threshold raised, so a second call of the same size allocates without talking
-// to the driver: a workflow calls backproject once per output block (focus.py:1988-2007), and
-// in a process that has enabled peer access (NCCL, multi-GPU) every plain cudaMalloc/cudaFree
-// has to map/unmap the allocation on all peers -- measured 850 ms per call for this path's
-// ~6 GB at 2 GPUs.  i3b_release_device_memory() hands the cached memory back.
-static void configure_pool(int device)
+// Device buffers are recycled through a small per-process cache instead of going back to the
+// driver after every call: a workflow calls backproject once per output block
+// (focus.py:1988-2007) with the same sizes, and in a process that has enabled peer access
+// (NCCL, multi-GPU) every cudaMalloc/cudaFree has to map/unmap the allocation on all peers --
+// measured 850 ms per call for this path's ~6 GB at 2 GPUs.  Buffers are returned to the cache
+// only after the streams that used them have been synchronised.  i3b_release_device_memory()
+// hands the cached memory back; I3B_POOL_KEEP_MB caps what is kept (0 = keep nothing).
+class DeviceCache {
+public:
+    void* get(size_t bytes)
+    {
+        int device = 0;
+        CK(cudaGetDevice(&device));
+        bytes = (bytes + kGranule - 1) / kGranule * kGranule;
+        {
+            std::lock_guard<std::mutex> lock(mtx_);
+            int best = -1;
+            for (int i = 0; i < (int) free_.size(); ++i) {
+                const Block& b = free_[i];
+                if (b.device != device || b.bytes < bytes || b.bytes > bytes + bytes / 4 + kGranule) continue;
+                if (best < 0 || b.bytes < free_[best].bytes) best = i;
+            }
+            if (best >= 0) {
+                Block b = free_[best];
+                free_.erase(free_.begin() + best);
+                cached_ -= b.bytes;
+                live_.push_back(b);
+                return b.p;
+            }
+        }
+        void* p = nullptr;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaErrorMemoryAllocation) { // make room and retry once
+            cudaGetLastError();
+            release_all();
+            e = cudaMalloc(&p, bytes);
+        }
+        CK(e);
+        std::lock_guard<std::mutex> lock(mtx_);
+        live_.push_back(Block {p, bytes, device});
+        return p;
+    }
+    void put(void* p)
+    {
+        Block b {nullptr, 0, 0};
+        {
+            std::lock_guard<std::mutex> lock(mtx_);
+            for (size_t i = 0; i < live_.size(); ++i)
+                if (live_[i].p == p) {
+                    b = live_[i];
+                    live_.erase(live_.begin() + i);
+                    break;
+                }
+            if (b.p && cached_ + b.bytes <= keep_limit()) {
+                free_.push_back(b);
+                cached_ += b.bytes;
+                return;
+            }
+        }
+        int cur = 0;
+        cudaGetDevice(&cur);
+        if (b.p && b.device != cur) cudaSetDevice(b.device);
+        cudaFree(p);
+        if (b.p && b.device != cur) cudaSetDevice(cur);
+    }
+    void release_all()
+    {
+        std::vector<Block> blocks;
+        {
+            std::lock_guard<std::mutex> lock(mtx_);
+            blocks.swap(free_);
+            cached_ = 0;
+        }
+        int cur = 0;
+        cudaGetDevice(&cur);
+        for (const Block& b : blocks) {
+            cudaSetDevice(b.device);
+            cudaFree(b.p);
+        }
+        cudaSetDevice(cur);
+    }
+
+private:
+    struct Block {
+        void* p;
+        size_t bytes;
+        int device;
+    };
+    static constexpr size_t kGranule = (size_t) 2 << 20;
+    static size_t keep_limit()
+    {
+        if (const char* e = std::getenv("I3B_POOL_KEEP_MB")) return (size_t) std::strtoull(e, nullptr, 10) << 20;
+        return ~(size_t) 0 >> 1;
+    }
+    std::mutex mtx_;
+    std::vector<Block> free_, live_;
+    size_t cached_ = 0;
+};
+
+static DeviceCache& device_cache()
 {
-    static std::mutex mtx;
-    static std::vector<int> done;
-    std::lock_guard<std::mutex> lock(mtx);
-    if (std::find(done.begin(), done.end(), device) != done.end()) return;
-    cudaMemPool_t pool;
-    CK(cudaDeviceGetDefaultMemPool(&pool, device));
-    unsigned long long threshold = ~0ull;
-    if (const char* e = std::getenv("I3B_POOL_KEEP_MB")) threshold = std::strtoull(e, nullptr, 10) << 20;
-    CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
-    done.push_back(device);
+    static DeviceCache* cache = new DeviceCache(); // leaked on purpose: no CUDA calls at exit
+    return *cache;
 }
 
 template<typename T>
 struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
-    cudaStream_t stream = nullptr; // allocation / release are ordered on this stream
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
     ~DevBuf() { release(); }
     void release()
     {
-        if (p) cudaFreeAsync(p, stream);
+        if (p) device_cache().put(p);
         p = nullptr;
         n = 0;
     }
-    void alloc(size_t count, cudaStream_t s)
+    void alloc(size_t count, cudaStream_t = nullptr)
     {
         release();
         n = count;
-        stream = s;
-        if (count) CK(cudaMallocAsync(&p, count * sizeof(T), s));
+        if (count) p = static_cast<T*>(device_cache().get(count * sizeof(T)));
     }
     void upload(const T* src, size_t count, cudaStream_t s)
     {
-        alloc(count, s);
+        alloc(count);
         if (count) CK(cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, s));
     }
 };
@@ -212,16 +295,12 @@ static DevKernel make_kernel(const I3B_Kernel& k, const float* data)
 struct Shard {
     int device = 0;
     int line0 = 0, nlines = 0;
-    // declared before the buffers: members are destroyed in reverse order, so the streams
-    // outlive the stream-ordered frees of the buffers below
+    // declared before the buffers (destroyed after them)
     struct Streams {
         cudaStream_t compute = nullptr, copy = nullptr;
         ~Streams()
         {
-            if (compute) {
-                cudaStreamSynchronize(compute); // drains the cudaFreeAsync of the buffers
-                cudaStreamDestroy(compute);
-            }
+            if (compute) cudaStreamDestroy(compute);
             if (copy) cudaStreamDestroy(copy);
         }
     } streams;
@@ -234,7 +313,7 @@ struct Shard {
     DevBuf<double2> acc;
     DevBuf<float2> out, rc;
     DevBuf<DevStatus> status;
-    DevBuf<unsigned char> tile_mask;
+    DevBuf<TileInfo> tile_info;
     const float2* rc_dev = nullptr; // staged lines (or the caller's device pointer)
     int rc_pitch = 0, rc_k0 = 0, rc_rows = 0;
     bool rc_resident = false;
@@ -249,8 +328,11 @@ struct Shard {
 
     ~Shard()
     {
-        // the buffers and streams are released right after this body, on this thread
+        // Buffers go back to the cache right after this body, on this thread: make sure
+        // nothing is still running on them (error paths may leave work in flight).
         if (compute || copy) cudaSetDevice(device);
+        if (compute) cudaStreamSynchronize(compute);
+        if (copy) cudaStreamSynchronize(copy);
     }
 };
 
@@ -270,12 +352,12 @@ static void shard_setup(const HostScene& hs, Shard& sh)
 {
     const I3B_BackprojectArgs& a = hs.a;
     CK(cudaSetDevice(sh.device));
-    cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, sh.device));
-    if (prop.major < 10)
-        throw ApiError(I3B_EXC_NO_DEVICE,
-                       std::string("device ") + prop.name + " is not sm_100-class; isce3_b200 has no fallback path");
-    configure_pool(sh.device);
+    // (cudaDeviceGetAttribute, not cudaGetDeviceProperties: the latter takes up to 100 ms)
+    int cc_major = 0;
+    CK(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, sh.device));
+    if (cc_major < 10)
+        throw ApiError(I3B_EXC_NO_DEVICE, "device " + std::to_string(sh.device) +
+                                                  " is not sm_100-class; isce3_b200 has no fallback path");
     CK(cudaStreamCreateWithFlags(&sh.compute, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&sh.copy, cudaStreamNonBlocking));
     cudaStream_t s = sh.compute;
@@ -333,7 +415,7 @@ static void shard_setup(const HostScene& hs, Shard& sh)
     sh.acc.alloc(npix, s);
     sh.out.alloc(npix, s);
     sh.height.alloc(npix, s);
-    sh.tile_mask.alloc((size_t) std::max(fast_tiles(sh.nlines, (int) og.grid.width), 1), s);
+    sh.tile_info.alloc((size_t) std::max(fast_tiles(sh.nlines, (int) og.grid.width), 1), s);
 
     AccumParams& A = sh.ap;
     std::memset(&A, 0, sizeof A);
@@ -349,6 +431,9 @@ static void shard_setup(const HostScene& hs, Shard& sh)
     A.kernel = make_kernel(a.kernel, sh.kdata.p);
     fast_tile_shape(&A.tile_az, &A.tile_rg);
     A.tiles_rg = (A.out_width + A.tile_rg - 1) / A.tile_rg;
+    P.tile_az = A.tile_az;
+    P.tile_rg = A.tile_rg;
+    P.tiles_rg = A.tiles_rg;
     sh.host_kernel = make_kernel(a.kernel, a.kernel.data);
     char why[160] = "";
     I3B_TapPolyFit fit;
@@ -372,16 +457,14 @@ static void shard_solve(const HostScene& hs, Shard& sh)
     e0.record(s);
     launch_pulse_table(sh.sp.in_orbit, sh.sp.in_time, hs.a.fc, sh.pulse.p + kPulsePadLo, sh.pv.p, sh.status.p, s);
     CK(cudaGetLastError());
-    if (sh.ap.npix > 0) {
-        launch_target_solve(sh.sp, sh.pix.p, sh.height.p, sh.status.p, s);
-        CK(cudaGetLastError());
-    }
+    launch_target_solve(sh.sp, sh.pix.p, sh.height.p, sh.tile_info.p, (int) sh.tile_info.n, sh.status.p, s);
+    CK(cudaGetLastError());
     e1.record(s);
     DevStatus st;
     CK(cudaMemcpyAsync(&st, sh.status.p, sizeof st, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     sh.stats.ms_target_solve = elapsed(e0, e1);
-    sh.stats.total_launches += 2;
+    sh.stats.total_launches += 3;
     sh.stats.pixel_pulses = (double) st.pixel_pulses;
     if (st.hard_error) throw ApiError(st.hard_error, "orbit interpolation outside of orbit domain");
     sh.status_code = st.soft_error;
@@ -405,19 +488,20 @@ static void shard_accumulate(Shard& sh, int k0, int k1, cudaStream_t s)
     A.tile_mask = nullptr;
     bool done = false;
     if (sh.use_fast) {
-        CK(cudaMemsetAsync(sh.tile_mask.p, 0, sh.tile_mask.n, s));
         const int rc = launch_accumulate_fast(A, sh.host_kernel, sh.pix.p, sh.pulse.p + kPulsePadLo, sh.rc_dev,
-                                              sh.acc.p, sh.tile_mask.p, sh.status.p, s);
+                                              sh.acc.p, sh.tile_info.p, sh.status.p, s);
         if (rc > 0) CK((cudaError_t) rc);
         if (rc == 0) {
             done = true;
             sh.stats.accumulate_launches += 1;
             sh.stats.total_launches += 1;
-            // tiles holding failed pixels were skipped: generic kernel on just those
-            A.tile_mask = sh.tile_mask.p;
-            launch_accumulate_generic(A, sh.pix.p, sh.pv.p, sh.rc_dev, sh.acc.p, s);
-            CK(cudaGetLastError());
-            sh.stats.total_launches += 1;
+            if (sh.status_code != 0) {
+                // tiles holding failed pixels were skipped: generic kernel on just those
+                A.tile_mask = sh.tile_info.p;
+                launch_accumulate_generic(A, sh.pix.p, sh.pv.p, sh.rc_dev, sh.acc.p, s);
+                CK(cudaGetLastError());
+                sh.stats.total_launches += 1;
+            }
         } else {
             sh.use_fast = false;
         }
@@ -458,10 +542,6 @@ static void shard_run(const HostScene& hs, Shard& sh, bool resident_only)
                 sh.rc_rows = klast - kfirst;
                 sh.rc.alloc((size_t) sh.rc_rows * sh.rc_pitch, s);
                 sh.rc_dev = sh.rc.p;
-                // the copy stream fills what the compute stream allocated
-                Event allocated;
-                allocated.record(s);
-                CK(cudaStreamWaitEvent(sh.copy, allocated.e, 0));
                 // pool memory is recycled: clear it, so that rows a pulse tile stages ahead of
                 // the landed slab (and the pad column) never hold stale bit patterns
                 CK(cudaMemsetAsync(sh.rc.p, 0, sh.rc.n * sizeof(float2), sh.copy));
@@ -475,6 +555,11 @@ static void shard_run(const HostScene& hs, Shard& sh, bool resident_only)
             const int slab = std::max(a.batch, 1);
             std::vector<std::unique_ptr<Event>> landed;
             const auto t0 = std::chrono::steady_clock::now();
+            // Slabs are copied back to back; an accumulation launch is issued for everything
+            // copied so far whenever the compute stream has run dry (and for the first and the
+            // last slab), so a fast host link gives 2 launches per call and a slow one a few
+            // more -- not one per slab, each of which would re-run every tile's prologue.
+            int pending = kfirst; // first pulse not yet covered by an accumulation launch
             for (int k = kfirst; k < klast; k += slab) {
                 const int rows = std::min(slab, klast - k);
                 CK(cudaMemcpy2DAsync(sh.rc.p + (size_t) (k - sh.rc_k0) * sh.rc_pitch,
@@ -483,9 +568,14 @@ static void shard_run(const HostScene& hs, Shard& sh, bool resident_only)
                                      devptr ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, sh.copy));
                 landed.emplace_back(new Event());
                 landed.back()->record(sh.copy);
-                CK(cudaStreamWaitEvent(s, landed.back()->e, 0));
                 sh.stats.h2d_bytes += (int64_t) rows * nr * (int64_t) sizeof(float2);
-                if (!resident_only) shard_accumulate(sh, k, k + rows, s);
+                if (resident_only) continue;
+                const bool first = k == kfirst, last = k + rows >= klast;
+                if (first || last || cudaStreamQuery(s) == cudaSuccess) {
+                    CK(cudaStreamWaitEvent(s, landed.back()->e, 0));
+                    shard_accumulate(sh, pending, k + rows, s);
+                    pending = k + rows;
+                }
             }
             CK(cudaStreamSynchronize(sh.copy));
             ms_h2d = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -816,12 +906,7 @@ int i3b_measure_peaks(int device, I3B_Peaks* peaks)
 int i3b_release_device_memory(void)
 {
     return guarded([&]() {
-        int n = 0;
-        if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
-        for (int d = 0; d < n; ++d) {
-            cudaMemPool_t pool;
-            if (cudaDeviceGetDefaultMemPool(&pool, d) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
-        }
+        device_cache().release_all();
         return 0;
     });
 }

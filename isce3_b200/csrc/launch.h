@@ -4,6 +4,15 @@
 
 namespace i3b {
 
+// Per fast-kernel tile summary written by the target solve: pulse span of the tile's pixels
+// and whether it holds a failed pixel (those tiles go to the generic kernel).  Lets an
+// accumulation launch skip tiles with no pulse in its range before touching pixel records.
+struct TileInfo {
+    int kmin, kmax; // over pixels with a non-empty aperture; kmin >= kmax: nothing to integrate
+    int bad;        // a pixel of the tile failed its geometry solve
+    int pad;
+};
+
 struct SolveParams {
     Linspace out_time, out_range, in_time;
     DevOrbit out_orbit, in_orbit;
@@ -16,6 +25,7 @@ struct SolveParams {
     int line0;     // first output line of this shard
     int out_lines; // lines in this shard
     int out_width;
+    int tile_az, tile_rg, tiles_rg; // fast-kernel tile grid of the shard
 };
 
 struct AccumParams {
@@ -31,15 +41,15 @@ struct AccumParams {
     double spacing_ratio;     // output / input range pixel spacing
     DevKernel kernel;         // data pointer: device memory
     // generic kernel only: when non-null, process just the pixels whose fast-kernel tile
-    // is flagged (tiles holding failed pixels are skipped by the fast kernel)
-    const unsigned char* tile_mask;
+    // is flagged bad (tiles holding failed pixels are skipped by the fast kernel)
+    const TileInfo* tile_mask;
     int tile_az, tile_rg, tiles_rg;
 };
 
 void launch_pulse_table(const DevOrbit& orbit, Linspace in_time, double fc, PulseRec* pulse,
                         double* pv, DevStatus* status, cudaStream_t s);
-void launch_target_solve(const SolveParams& P, PixelRec* pix, float* height, DevStatus* status,
-                         cudaStream_t s);
+void launch_target_solve(const SolveParams& P, PixelRec* pix, float* height, TileInfo* tiles,
+                         int n_tiles, DevStatus* status, cudaStream_t s);
 void launch_accumulate_generic(const AccumParams& P, const PixelRec* pix, const double* pv,
                                const float2* rc, double2* acc, cudaStream_t s);
 void launch_finalize(long long npix, const PixelRec* pix, const double2* acc, float2* out,
@@ -50,7 +60,7 @@ void launch_finalize(long long npix, const PixelRec* pix, const double2* acc, fl
 bool fast_supported(const DevKernel& host_kernel, char* why, size_t why_len);
 int launch_accumulate_fast(const AccumParams& P, const DevKernel& host_kernel,
                            const PixelRec* pix, const PulseRec* pulse, const float2* rc,
-                           double2* acc, unsigned char* tile_generic, DevStatus* status,
+                           double2* acc, const TileInfo* tiles, DevStatus* status,
                            cudaStream_t s);
 int fast_fit(const DevKernel& host_kernel, I3B_TapPolyFit* fit, char* why, size_t why_len);
 int fast_tiles(int out_lines, int out_width);

@@ -47,9 +47,15 @@ __global__ void pulse_table_kernel(DevOrbit orbit, Linspace in_time, double fc, 
 // geometry, LLH, geo2rdr_bracket on the input geometry, CPI bounds, dry-troposphere
 // delay) fused into one kernel that writes a 40-byte record per pixel instead of the
 // reference CUDA path's ~136 B of FP64 side tables (cuda/focus/Backproject.cu:526-640).
+__global__ void tile_info_init_kernel(TileInfo* tiles, int n)
+{
+    const int i = (int) (blockIdx.x * blockDim.x + threadIdx.x);
+    if (i < n) tiles[i] = TileInfo {INT_MAX, INT_MIN, 0, 0};
+}
+
 __global__ void __launch_bounds__(128)
 target_solve_kernel(SolveParams P, PixelRec* __restrict__ pix, float* __restrict__ height,
-                    DevStatus* status)
+                    TileInfo* __restrict__ tiles, DevStatus* status)
 {
     const long long tid = (long long) blockIdx.x * blockDim.x + threadIdx.x;
     const long long npix = (long long) P.out_lines * P.out_width;
@@ -103,6 +109,34 @@ target_solve_kernel(SolveParams P, PixelRec* __restrict__ pix, float* __restrict
     // block-level reduction of the pulse span and the work count
     int kmin = (kstart >= 0 && kstop > kstart) ? kstart : INT_MAX;
     int kmax = (kstart >= 0 && kstop > kstart) ? kstop : INT_MIN;
+    // per-tile summary: one atomic set per group of lanes that share a tile
+    {
+        int tile = -1;
+        if (tid < npix) {
+            const int jl = (int) (tid / P.out_width), i = (int) (tid % P.out_width);
+            tile = (jl / P.tile_az) * P.tiles_rg + i / P.tile_rg;
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, tile);
+        int tmin = kmin, tmax = kmax, tbad = (tid < npix && kstart < 0) ? 1 : 0;
+        // reduce over the peer group (lanes of one tile are contiguous in a warp, but stay general)
+        for (int o = 16; o > 0; o >>= 1) {
+            const int src = (threadIdx.x & 31) ^ o;
+            const int omin = __shfl_xor_sync(0xffffffffu, tmin, o);
+            const int omax = __shfl_xor_sync(0xffffffffu, tmax, o);
+            const int obad = __shfl_xor_sync(0xffffffffu, tbad, o);
+            if (peers & (1u << src)) {
+                tmin = min(tmin, omin);
+                tmax = max(tmax, omax);
+                tbad |= obad;
+            }
+        }
+        const int leader = __ffs(peers) - 1;
+        if (tile >= 0 && (int) (threadIdx.x & 31) == leader) {
+            if (tmin != INT_MAX) atomicMin(&tiles[tile].kmin, tmin);
+            if (tmax != INT_MIN) atomicMax(&tiles[tile].kmax, tmax);
+            if (tbad) atomicOr(&tiles[tile].bad, 1);
+        }
+    }
     unsigned long long pp = (kstart >= 0) ? (unsigned long long) (kstop - kstart) : 0ull;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -130,7 +164,7 @@ accumulate_generic_kernel(AccumParams P, const PixelRec* __restrict__ pix,
     if (tid >= P.npix) return;
     if (P.tile_mask) {
         const int j = (int) (tid / P.out_width), i = (int) (tid % P.out_width);
-        if (!P.tile_mask[(j / P.tile_az) * P.tiles_rg + (i / P.tile_rg)]) return;
+        if (!P.tile_mask[(j / P.tile_az) * P.tiles_rg + (i / P.tile_rg)].bad) return;
     }
     const PixelRec rec = pix[tid];
     if (rec.kstart < 0) return;
@@ -196,12 +230,14 @@ void launch_pulse_table(const DevOrbit& orbit, Linspace in_time, double fc, Puls
     pulse_table_kernel<<<(n + 127) / 128, 128, 0, s>>>(orbit, in_time, fc, pulse, pv, status);
 }
 
-void launch_target_solve(const SolveParams& P, PixelRec* pix, float* height, DevStatus* status,
-                         cudaStream_t s)
+void launch_target_solve(const SolveParams& P, PixelRec* pix, float* height, TileInfo* tiles,
+                         int n_tiles, DevStatus* status, cudaStream_t s)
 {
+    tile_info_init_kernel<<<(n_tiles + 255) / 256, 256, 0, s>>>(tiles, n_tiles);
     const long long npix = (long long) P.out_lines * P.out_width;
+    if (npix == 0) return;
     const unsigned grid = (unsigned) ((npix + 127) / 128);
-    target_solve_kernel<<<grid, 128, 0, s>>>(P, pix, height, status);
+    target_solve_kernel<<<grid, 128, 0, s>>>(P, pix, height, tiles, status);
 }
 
 void launch_accumulate_generic(const AccumParams& P, const PixelRec* pix, const double* pv,

@@ -17,7 +17,7 @@ out = torch.empty(shape, dtype=torch.complex64, pin_memory=True).numpy()
 args = list(sc.backproject_args())
 for host, name in ((pin, "pinned"), (sc.rc, "pageable")):
     args[1] = host
-    for it in range(3):
+    for it in range(5):
         t = time.perf_counter()
         backproject(out, *args)
         dt = (time.perf_counter() - t) * 1e3
