@@ -314,6 +314,22 @@ def test_azimuth_sharding_over_device_list(oracle):
     check(many, run_cpu(oracle, sc), sc)
 
 
+def test_azimuth_sharding_over_two_gpus(oracle):
+    """devices=[0, 1]: one azimuth block per GPU, each fed only the pulses its block needs,
+    results gathered on the host with no inter-GPU exchange (skipped on a 1-GPU box)."""
+    from isce3_b200 import _capi
+    if _capi.load_library().i3b_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    sc = synth.make_scene("c2", pulses=3072, bins=1024, out_lines=50, out_samples=260, n_targets=1)
+    one = run_gpu(sc)
+    two = run_gpu(sc, devices=[0, 1])
+    assert two[3]["n_devices"] == 2
+    assert two[3]["pixel_pulses"] == one[3]["pixel_pulses"]
+    np.testing.assert_allclose(two[1], one[1], rtol=0, atol=1e-5 * np.abs(one[1]).max())
+    np.testing.assert_array_equal(two[2], one[2])
+    check(two, run_cpu(oracle, sc), sc)
+
+
 def test_full_c1_properties():
     """BASELINE.json configs[0] at full size (2048 x 4096 -> 512 x 512), checked through
     size-independent properties: the target focuses at its pixel with gain = #pulses,
