@@ -385,6 +385,36 @@ def run_ours(args):
                          f"({pp_cpu:.3g} pixel*pulses, {dt:.1f} s)",
                "rel_rms_gpu_vs_cpu_on_sample": parity}
 
+    # ---- same-GPU comparator: the reference's own CUDA backprojection (reduced harness) ---
+    ref_cuda = None
+    if not args.no_ref_cuda and world == 1:
+        try:
+            from oracle import tdbp
+            if tdbp.have_ref_cuda() and not sc.dem.have_raster:
+                rcu = tdbp.ref_cuda()
+                small = sc.out_subgrid(0, min(8, shape[0]))
+                rcu.backproject(np.zeros((min(8, shape[0]), shape[1]), np.complex64), small, rc_host,
+                                *common, batch=args.batch)  # module load / first-call costs
+                ref_out = np.empty(shape, np.complex64)
+                t0 = time.perf_counter()
+                rcu.backproject(ref_out, sub, rc_host, *common, batch=args.batch)
+                dt = time.perf_counter() - t0
+                m = np.isfinite(ref_out) & np.isfinite(out_host)
+                ref_cuda = {
+                    "value": pp_rank / dt, "unit": UNIT, "ms": 1e3 * dt, "kind": rcu.kind,
+                    "what": "isce3::cuda::focus::backproject (cuda/focus/Backproject.cu, unmodified) "
+                            "on the same frame, same host buffers, one call, wall time",
+                    "e2e_speedup_of_this_repo": e2e_value / (pp_rank / dt),
+                    "rel_rms_ours_vs_reference_cuda": float(
+                        np.linalg.norm((out_host - ref_out)[m]) / max(np.linalg.norm(ref_out[m]), 1e-30)),
+                }
+            elif sc.dem.have_raster:
+                ref_cuda = {"unavailable": "reduced harness supports constant-height DEMs only"}
+            else:
+                ref_cuda = {"unavailable": "oracle/_ref/libtdbp_refcuda.so not built"}
+        except Exception as exc:  # the comparator must never take the bench down
+            ref_cuda = {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -398,7 +428,7 @@ def run_ours(args):
                 "ms_per_step": 1e3 * e2e_elapsed / args.steps,
                 "max_abs_diff_vs_resident": same},
         "gpu_launches": int(launches),
-        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "reference_cuda": ref_cuda,
         "target_solve_ms_per_step": solve_ms / args.steps,
     }
     print(json.dumps(line), flush=True)
@@ -418,6 +448,8 @@ def main():
     ap.add_argument("--taps", type=int, default=0)
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-ref-cuda", action="store_true",
+                    help="skip the reference-CUDA comparator (one ~8 s call at C2)")
     args = ap.parse_args()
     args.warmup_ref = min(args.warmup, 1)
     if args.impl == "reference":

@@ -25,6 +25,7 @@ from isce3_b200.focus import build_args
 HERE = Path(__file__).resolve().parent
 PORT_LIB = HERE / "libtdbp_oracle.so"
 REF_LIB = HERE / "_ref" / "libtdbp_ref.so"
+REFCUDA_LIB = HERE / "_ref" / "libtdbp_refcuda.so"
 
 BRENT_FN = C.CFUNCTYPE(C.c_double, C.c_double, C.c_void_p)
 
@@ -215,6 +216,44 @@ def ref() -> Oracle:
             raise FileNotFoundError(f"{REF_LIB} not built (needs /root/reference; `make -C oracle ref`)")
         _cache["ref"] = Oracle(REF_LIB, "tdbp_ref")
     return _cache["ref"]
+
+
+class ReferenceCuda:
+    """The reference's own CUDA backprojection (cuda/focus/Backproject.cu, unmodified) in the
+    reduced harness of oracle/cuda_ref: constant-height DEM and no-data Doppler LUTs only.
+    A same-GPU comparator for bench.py and a cross-check in tests/ -- never a product path."""
+
+    kind = "reference CUDA kernels, reduced harness"
+
+    def __init__(self, path: Path = REFCUDA_LIB):
+        self.lib = C.CDLL(str(path))
+        self._backproject = self.lib.tdbp_refcuda_backproject
+        self._backproject.restype = C.c_int
+        self._backproject.argtypes = [C.POINTER(_capi.BackprojectArgs)]
+        self.lib.tdbp_refcuda_last_error.restype = C.c_char_p
+
+    def backproject(self, out, out_geometry, in_, in_geometry, dem, fc, ds, kernel,
+                    dry_tropo_model="tsx", rdr2geo_params=None, geo2rdr_params=None, batch=1024,
+                    height=None):
+        fl = build_args(out, out_geometry, in_, in_geometry, dem, fc, ds, kernel,
+                        dry_tropo_model, rdr2geo_params, geo2rdr_params, batch, height)
+        status = self._backproject(C.byref(fl.args))
+        if status < 0:
+            raise RuntimeError(f"reference CUDA status {status}: "
+                               f"{(self.lib.tdbp_refcuda_last_error() or b'').decode()}")
+        return status != 0
+
+
+def have_ref_cuda() -> bool:
+    return REFCUDA_LIB.exists()
+
+
+def ref_cuda() -> ReferenceCuda:
+    if "refcuda" not in _cache:
+        if not REFCUDA_LIB.exists():
+            raise FileNotFoundError(f"{REFCUDA_LIB} not built (`make -C oracle refcuda`)")
+        _cache["refcuda"] = ReferenceCuda()
+    return _cache["refcuda"]
 
 
 def best() -> Oracle:

@@ -330,6 +330,24 @@ def test_azimuth_sharding_over_two_gpus(oracle):
     check(two, run_cpu(oracle, sc), sc)
 
 
+def test_reference_cuda_comparator_agrees(oracle):
+    """The reference's own CUDA backprojection (oracle/_ref/libtdbp_refcuda.so, reduced
+    harness) on the same inputs: it is the same-GPU baseline of bench.py, so check that it
+    really computes the same image as the CPU reference and as this repo's kernels."""
+    from oracle import tdbp
+    if not tdbp.have_ref_cuda():
+        pytest.skip("oracle/_ref/libtdbp_refcuda.so not built")
+    sc = synth.make_scene("c2", pulses=4096, bins=1024, out_lines=24, out_samples=200, n_targets=1)
+    ref = np.zeros(shape_of(sc), np.complex64)
+    href = np.zeros(shape_of(sc), np.float32)
+    assert tdbp.ref_cuda().backproject(ref, *sc.backproject_args(), height=href) is False
+    gpu = run_gpu(sc)
+    cpu = run_cpu(oracle, sc)
+    assert np.linalg.norm(ref - cpu[1]) <= 1e-5 * np.linalg.norm(cpu[1])
+    assert np.linalg.norm(ref - gpu[1]) <= RMS_TOL * np.linalg.norm(ref)
+    assert np.max(np.abs(href - cpu[2])) <= 1e-3
+
+
 def test_full_c1_properties():
     """BASELINE.json configs[0] at full size (2048 x 4096 -> 512 x 512), checked through
     size-independent properties: the target focuses at its pixel with gain = #pulses,
