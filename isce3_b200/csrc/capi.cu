@@ -230,7 +230,10 @@ static void validate(const I3B_BackprojectArgs& a)
     }
     if (a.dem.have_raster) {
         if (!a.dem.data || a.dem.length < 4 || a.dem.width < 4) bad("DEM raster too small");
-        if (a.dem.epsg != 4326) bad("raster DEMs are supported for EPSG:4326 only");
+        DevProj pj;
+        if (!proj_setup(a.dem.epsg, kA, kE2, &pj))
+            bad("unknown EPSG code for a raster DEM: " + std::to_string(a.dem.epsg) +
+                " (supported: 4326, UTM 326xx/327xx, 3031, 3413, 6933)");
         if (a.dem.method == I3B_INTERP_SINC) bad("sinc DEM interpolation is not supported");
     }
     if (!(a.fc > 0) || !(a.ds > 0)) bad("fc and ds must be positive");
@@ -394,6 +397,7 @@ static void shard_setup(const HostScene& hs, Shard& sh)
     P.dem.length = (int) a.dem.length; P.dem.width = (int) a.dem.width;
     P.dem.ref_height = a.dem.ref_height; P.dem.xstart = a.dem.xstart; P.dem.ystart = a.dem.ystart;
     P.dem.dx = a.dem.dx; P.dem.dy = a.dem.dy; P.dem.data = sh.dem.p;
+    proj_setup(a.dem.have_raster ? a.dem.epsg : 4326, kA, kE2, &P.dem.proj);
     P.r2g = a.rdr2geo;
     P.g2r = a.geo2rdr;
     P.wvl = kC / a.fc; // Backproject.cpp:119: wavelength from fc, not from the grid

@@ -11,6 +11,7 @@
 #include <cstdint>
 
 #include "../../include/isce3_b200_backproject.h"
+#include "projections.cuh"
 
 namespace i3b {
 
@@ -54,6 +55,7 @@ struct DevDEM {
     int length, width;
     double ref_height, xstart, ystart, dx, dy;
     const float* data;
+    DevProj proj; // forward projection of the raster's CRS (set up on the host)
 };
 
 struct DevKernel {

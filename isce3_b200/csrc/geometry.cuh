@@ -333,17 +333,24 @@ __device__ inline double lut2d_eval(const DevLUT2d& l, double y, double x)
     return interp2d<double>(l.method, xi, yi, g);
 }
 
+// DEMInterpolator::interpolateLonLat -> interpolateXY (DEMInterpolator.cpp:592-659): project
+// to the raster's CRS, then sample; the longitude wrapping applies to EPSG:4326 only.
 __device__ inline double dem_interp_lonlat(const DevDEM& d, double lon, double lat)
 {
     if (!d.have_raster) return d.ref_height;
-    double x = lon * 180.0 / M_PI; // LonLat::forward, core/Projections.h:127-133
-    const double y = lat * 180.0 / M_PI;
-    if (x > 360 || x < -360) x = fmod(x, 360.);
-    if (x < -180) x += 360;
-    if (x - 360 >= d.xstart) {
-        x -= 360;
-    } else if (x < d.xstart && x + 360 >= d.xstart) {
-        x += 360;
+    double x, y;
+    // (the reference ignores forward()'s status and samples an unset point: out of the raster)
+    if (proj_forward(d.proj, lon, lat, &x, &y) != 0) return d.ref_height;
+    if (d.proj.kind == PROJ_LONLAT) {
+        if (x > 360 || x < -360) x = fmod(x, 360.);
+        if (x < -180) x += 360;
+        if (x - 360 >= d.xstart) {
+            x -= 360;
+        } else if (x < d.xstart && x + 360 >= d.xstart) {
+            x += 360;
+        } else if (x < d.xstart) {
+            return d.ref_height;
+        }
     } else if (x < d.xstart) {
         return d.ref_height;
     }

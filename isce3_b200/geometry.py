@@ -23,12 +23,14 @@ class DEMInterpolator:
     def from_array(cls, data, x_start, y_start, delta_x, delta_y, epsg=4326,
                    method="biquintic", ref_height=None):
         """Raster DEM: data[row, col] at (x_start + col*delta_x, y_start + row*delta_y),
-        pixel centres, x = longitude / y = latitude in degrees for EPSG:4326."""
+        pixel centres; x = longitude / y = latitude in degrees for EPSG:4326, projected metres
+        for the other codes createProj knows (UTM 326xx/327xx, 3031, 3413, 6933;
+        core/Projections.cpp:373-402)."""
         data = np.ascontiguousarray(data, dtype=np.float32)
         if data.ndim != 2:
             raise ValueError("DEM raster must be 2-D")
-        if int(epsg) != 4326:
-            raise ValueError("raster DEMs are supported for EPSG:4326 only")
+        from .projections import make_projection
+        make_projection(int(epsg))  # raises for codes createProj does not know
         self = cls(float(np.mean(data)) if ref_height is None else ref_height, method, epsg)
         if self.interp_method == DataInterpMethod.SINC:
             raise ValueError("sinc DEM interpolation is not supported on the TDBP path")

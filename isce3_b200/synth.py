@@ -269,6 +269,23 @@ def synthetic_dem(lon_c, lat_c, half_extent_deg, posting_deg=1.0 / 3600, hmin=0.
                                       -posting_deg, 4326, method)
 
 
+def synthetic_dem_projected(epsg, lon_c, lat_c, half_extent_m, posting_m=30.0, hmin=0.0, hmax=2000.0,
+                            method="biquintic"):
+    """Same kind of smooth relief on a grid of projected coordinates (UTM / polar
+    stereographic / EASE-2), north-up, centred on (lon_c, lat_c) [radians]."""
+    from .projections import make_projection
+    xc, yc = make_projection(epsg).forward(lon_c, lat_c)
+    n = int(round(2 * half_extent_m / posting_m)) + 1
+    x = xc - half_extent_m + np.arange(n) * posting_m
+    y = yc + half_extent_m - np.arange(n) * posting_m
+    X, Y = x[None, :] - xc, y[:, None] - yc
+    z = (np.sin(2 * np.pi * X / 31e3) * np.cos(2 * np.pi * Y / 23e3) +
+         0.5 * np.sin(2 * np.pi * (X + Y) / 11e3) + 0.25 * np.cos(2 * np.pi * (X - 2 * Y) / 7e3))
+    h = hmin + (hmax - hmin) * (z + 1.75) / 3.5
+    return DEMInterpolator.from_array(h.astype(np.float32), x[0], y[0], posting_m, -posting_m,
+                                      epsg, method)
+
+
 def dem_height_fn(hmin=0.0, hmax=2000.0):
     def f(lon, lat):
         lon_d, lat_d = np.degrees(lon), np.degrees(lat)
@@ -284,9 +301,13 @@ def _dem_sample_fn(dem: DEMInterpolator):
     if not dem.have_raster:
         return lambda lon, lat: dem.ref_height
 
+    from .projections import make_projection
+    proj = make_projection(dem.epsg_code)
+
     def f(lon, lat):
-        col = (math.degrees(lon) - dem.x_start) / dem.delta_x
-        row = (math.degrees(lat) - dem.y_start) / dem.delta_y
+        x, y = proj.forward(lon, lat)
+        col = (x - dem.x_start) / dem.delta_x
+        row = (y - dem.y_start) / dem.delta_y
         c0, r0 = int(math.floor(col)), int(math.floor(row))
         if r0 < 2 or r0 >= dem.length - 1 or c0 < 2 or c0 >= dem.width - 1:
             return dem.ref_height  # same margin rule as DEMInterpolator.cpp:649-653
@@ -300,8 +321,11 @@ def _dem_sample_fn(dem: DEMInterpolator):
 def make_scene(name="c1", *, pulses=None, bins=None, out_lines=None, out_samples=None,
                n_targets=None, noise_db=None, taps=None, seed=1234, dry_tropo_model=None,
                with_dem=None, ds=None, table_size=2048, doppler_lut=False,
-               look_side=LookSide.Left, out_range_spacing_ratio=1.0, out_prf_ratio=1.0):
-    """Build one of the named synthetic configurations (see module docstring)."""
+               look_side=LookSide.Left, out_range_spacing_ratio=1.0, out_prf_ratio=1.0,
+               dem_epsg=None):
+    """Build one of the named synthetic configurations (see module docstring).
+    ``dem_epsg``: CRS of the raster DEM (configurations with relief): None / 4326, "utm" (the
+    zone of the scene centre) or an EPSG code createProj knows (3031, 3413, 6933, 326xx...)."""
     base = name.lower()
     airborne = base.startswith("c5")
     fc = 1.2575e9
@@ -376,7 +400,12 @@ def make_scene(name="c1", *, pulses=None, bins=None, out_lines=None, out_samples
         ctr = ecef_to_llh(zero_doppler_target(orbit, t_mid, r_mid, look_side, lambda lo, la: 1000.0))
         swath_m = max(nbins * dr / math.sin(math.radians(30.0)), duration * speed) * 0.5 + 3.0e4
         half_deg = math.degrees(swath_m / A_WGS84) / max(math.cos(ctr[1]), 0.2)
-        dem = synthetic_dem(math.degrees(ctr[0]), math.degrees(ctr[1]), min(half_deg, 3.0))
+        if dem_epsg in (None, 4326):
+            dem = synthetic_dem(math.degrees(ctr[0]), math.degrees(ctr[1]), min(half_deg, 3.0))
+        else:
+            from .projections import utm_epsg_for
+            code = utm_epsg_for(ctr[0], ctr[1]) if dem_epsg == "utm" else int(dem_epsg)
+            dem = synthetic_dem_projected(code, ctr[0], ctr[1], min(swath_m, 3.0e5))
     else:
         dem = DEMInterpolator(0.0)
     hfn = _dem_sample_fn(dem)

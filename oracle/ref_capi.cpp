@@ -16,7 +16,7 @@
 //
 // What is NOT the reference's own code in this library: the headers under
 // oracle/shim/ (fixed-size vector algebra standing in for Eigen 3.3.7, and
-// LUT2d / DEMInterpolator / Projections classes backed by the restated
+// LUT2d / DEMInterpolator classes backed by the restated
 // samplers of oracle/tdbp_samplers.h), because Eigen, GDAL and pyre are absent
 // from this image.  This file only flattens/unflattens arguments.
 #include <cmath>
@@ -34,6 +34,7 @@
 #include <isce3/core/Kernels.h>
 #include <isce3/core/LUT2d.h>
 #include <isce3/core/Orbit.h>
+#include <isce3/core/Projections.h>
 #include <isce3/core/TimeDelta.h>
 #include <isce3/error/ErrorCode.h>
 #include <isce3/except/Error.h>
@@ -356,6 +357,19 @@ int tdbp_ref_brent(double a, double b, double (*f)(double, void*), void* ctx, do
 double tdbp_ref_lut2d_eval(const I3B_LUT2d* l, double y, double x)
 {
     return LUT2d<double>(*l).eval(y, x);
+}
+
+// core/Projections.cpp: createProj(epsg)->forward  (lon, lat in radians)
+int tdbp_ref_project_forward(int epsg, double lon, double lat, double* xy)
+{
+    return guarded([&]() {
+        std::unique_ptr<ProjectionBase> pj(createProj(epsg));
+        Vec3 out;
+        const int st = pj->forward(Vec3(lon, lat, 0.0), out);
+        xy[0] = out[0];
+        xy[1] = out[1];
+        return st;
+    });
 }
 
 double tdbp_ref_dem_interp(const I3B_DEM* d, double lon, double lat)

@@ -67,6 +67,7 @@ class Oracle:
                         C.c_double, dp)
         self._lut = f("lut2d_eval", C.c_double, P(_capi.LUT2d), C.c_double, C.c_double)
         self._dem = f("dem_interp", C.c_double, P(_capi.DEM), C.c_double, C.c_double)
+        self._proj = f("project_forward", C.c_int, C.c_int, C.c_double, C.c_double, dp)
         self._last_error = f("last_error", C.c_char_p)
         self._backproject_pp = None
         if prefix == "tdbp_oracle":
@@ -188,6 +189,12 @@ class Oracle:
         fl = _capi.Flattened()
         l = _capi.flatten_lut2d(lut, fl)
         return self._lut(C.byref(l), y, x)
+
+    def project_forward(self, epsg, lon, lat):
+        """(status, x, y) of createProj(epsg)->forward for lon, lat in radians."""
+        xy, xp = self._v3(np.zeros(3))
+        st = self._proj(int(epsg), float(lon), float(lat), xp)
+        return st, xy[0], xy[1]
 
     def dem_interp(self, dem, lon, lat):
         fl = _capi.Flattened()

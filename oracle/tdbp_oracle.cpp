@@ -771,6 +771,11 @@ double tdbp_oracle_lut2d_eval(const I3B_LUT2d* l, double y, double x)
     return lut2d_eval(*l, y, x);
 }
 
+int tdbp_oracle_project_forward(int epsg, double lon, double lat, double* xy)
+{
+    return proj::forward(epsg, lon, lat, &xy[0], &xy[1]);
+}
+
 double tdbp_oracle_dem_interp(const I3B_DEM* d, double lon, double lat)
 {
     return dem_interp_lonlat(*d, lon, lat);

@@ -192,13 +192,133 @@ inline double dem_interp_xy(const I3B_DEM& d, double x, double y)
     return interp2d<float>(d.method, col, row, g);
 }
 
-// DEMInterpolator.cpp:592-611 with LonLat::forward (Projections.h:127-133).
-// Only EPSG:4326 rasters are supported by the oracle.
+// ---- map projections (forward only): restatement of cxx/isce3/core/Projections.cpp -------
+// createProj :373-402, UTM ctor/forward :84-213, PolarStereo :247-297, CEA :324-360.
+// The oracle/_ref build does NOT use these: its DEMInterpolator shim calls the reference's
+// own createProj()->forward() (Projections.cpp compiled unchanged).
+namespace proj {
+
+// Projections.cpp:36-46
+inline double clens(const double* a, int size, double real)
+{
+    const double* p;
+    double hr, hr1, hr2;
+    for (p = a + size, hr2 = 0., hr1 = *(--p), hr = 0.; a - p; hr2 = hr1, hr1 = hr)
+        hr = -hr2 + (2. * hr1 * std::cos(real)) + *(--p);
+    return std::sin(real) * hr;
+}
+
+// Projections.cpp:58-82
+inline double clenS(const double* a, int size, double real, double imag, double& R, double& I)
+{
+    const double* p;
+    double hr, hr1, hr2, hi, hi1, hi2;
+    for (p = a + size, hr2 = 0., hi2 = 0., hi1 = 0., hr1 = *(--p), hr = 0., hi = 0.; a - p;
+         hr2 = hr1, hi2 = hi1, hr1 = hr, hi1 = hi) {
+        hr = -hr2 + (2. * hr1 * std::cos(real) * std::cosh(imag)) -
+             (-2. * hi1 * std::sin(real) * std::sinh(imag)) + *(--p);
+        hi = -hi2 + (-2. * hr1 * std::sin(real) * std::sinh(imag)) +
+             (2. * hi1 * std::cos(real) * std::cosh(imag));
+    }
+    R = (std::sin(real) * std::cosh(imag) * hr) - (std::cos(real) * std::sinh(imag) * hi);
+    I = (std::sin(real) * std::cosh(imag) * hi) + (std::cos(real) * std::sinh(imag) * hr);
+    return R;
+}
+
+inline double pj_tsfn(double phi, double sinphi, double e)
+{
+    sinphi *= e;
+    return std::tan(.5 * ((.5 * M_PI) - phi)) / std::pow((1. - sinphi) / (1. + sinphi), .5 * e);
+}
+
+inline double pj_qsfn(double sinphi, double e, double one_es)
+{
+    const double con = e * sinphi;
+    return one_es * ((sinphi / (1. - std::pow(con, 2))) - ((.5 / e) * std::log((1. - con) / (1. + con))));
+}
+
+constexpr double kA = 6378137.0, kE2 = 0.006694379990141317;
+
+// returns 0 on success, 1 where the reference's forward() fails, -1 for an unknown code
+inline int forward(int epsg, double lon, double lat, double* x, double* y)
+{
+    if (epsg == 4326) {
+        *x = lon * 180.0 / M_PI;
+        *y = lat * 180.0 / M_PI;
+        return 0;
+    }
+    if (epsg > 32600 && epsg < 32800) {
+        int zone;
+        bool isnorth;
+        if (epsg <= 32660) { zone = epsg - 32600; isnorth = true; }
+        else if (epsg > 32700 && epsg <= 32760) { zone = epsg - 32700; isnorth = false; }
+        else return -1;
+        const double lon0 = ((zone - 0.5) * (M_PI / 30.)) - M_PI;
+        const double f = kE2 / (1. + std::sqrt(1 - kE2));
+        const double n = f / (2. - f);
+        double cbg[6], gtu[6];
+        cbg[0] = n * (-2 + n * ((2. / 3.) + n * ((4. / 3.) + n * ((-82. / 45.) + n * ((32. / 45.) + n * (4642. / 4725.))))));
+        cbg[1] = std::pow(n, 2) * ((5. / 3.) + n * ((-16. / 15.) + n * ((-13. / 9.) + n * ((904. / 315.) + n * (-1522. / 945.)))));
+        cbg[2] = std::pow(n, 3) * ((-26. / 15.) + n * ((34. / 21.) + n * ((8. / 5.) + n * (-12686. / 2835.))));
+        cbg[3] = std::pow(n, 4) * ((1237. / 630.) + n * ((-12. / 5.) + n * (-24832. / 14175.)));
+        cbg[4] = std::pow(n, 5) * ((-734. / 315.) + n * (109598. / 31185.));
+        cbg[5] = std::pow(n, 6) * (444337. / 155925.);
+        const double Qn = (0.9996 / (1. + n)) * (1. + n * n * ((1. / 4.) + n * n * ((1. / 64.) + ((n * n) / 256.))));
+        gtu[0] = n * (.5 + n * ((-2. / 3.) + n * ((5. / 16.) + n * ((41. / 180.) + n * ((-127. / 288.) + n * (7891. / 37800.))))));
+        gtu[1] = std::pow(n, 2) * ((13. / 48.) + n * ((-3. / 5.) + n * ((557. / 1440.) + n * ((281. / 630.) + n * (-1983433. / 1935360.)))));
+        gtu[2] = std::pow(n, 3) * ((61. / 240.) + n * ((-103. / 140.) + n * ((15061. / 26880.) + n * (167603. / 181440.))));
+        gtu[3] = std::pow(n, 4) * ((49561. / 161280.) + n * ((-179. / 168.) + n * (6601661. / 7257600.)));
+        gtu[4] = std::pow(n, 5) * ((34729. / 80640.) + n * (-3418889. / 1995840.));
+        gtu[5] = std::pow(n, 6) * (212378941. / 319334400.);
+        const double Z = clens(cbg, 6, 0.);
+        const double Zb = -Qn * (Z + clens(gtu, 6, 2 * Z));
+        const double gauss = clens(cbg, 6, 2. * lat) + lat;
+        const double lam = lon - lon0;
+        double Cn = std::atan2(std::sin(gauss), std::cos(lam) * std::cos(gauss));
+        double Ce = std::atan2(std::sin(lam) * std::cos(gauss),
+                               std::hypot(std::sin(gauss), std::cos(gauss) * std::cos(lam)));
+        Ce = std::asinh(std::tan(Ce));
+        double dCn, dCe;
+        Cn += clenS(gtu, 6, 2 * Cn, 2 * Ce, dCn, dCe);
+        Ce += dCe;
+        if (std::fabs(Ce) > 2.623395162778) return 1;
+        *x = (Qn * Ce * kA) + 500000.;
+        *y = (((Qn * Cn) + Zb) * kA) + (isnorth ? 0. : 10000000.);
+        return 0;
+    }
+    if (epsg == 3031 || epsg == 3413) {
+        const bool isnorth = epsg == 3413;
+        const double lat_ts = (isnorth ? 70. : 71.) * M_PI / 180.;
+        const double lon0 = isnorth ? -45. * (M_PI / 180.) : 0.;
+        const double e = std::sqrt(kE2);
+        double akm1 = std::cos(lat_ts) / pj_tsfn(lat_ts, std::sin(lat_ts), e);
+        akm1 *= kA / std::sqrt(1. - (std::pow(e, 2) * std::pow(std::sin(lat_ts), 2)));
+        const double lam = lon - lon0;
+        const double phi = lat * (isnorth ? 1. : -1.);
+        const double temp = akm1 * pj_tsfn(phi, std::sin(phi), e);
+        *x = temp * std::sin(lam);
+        *y = -temp * std::cos(lam) * (isnorth ? 1. : -1.);
+        return 0;
+    }
+    if (epsg == 6933) {
+        const double lat_ts = M_PI / 6.;
+        const double k0 = std::cos(lat_ts) / std::sqrt(1. - (kE2 * std::pow(std::sin(lat_ts), 2)));
+        const double e = std::sqrt(kE2), one_es = 1. - kE2;
+        *x = k0 * lon * kA;
+        *y = (.5 * kA * pj_qsfn(std::sin(lat), e, one_es)) / k0;
+        return 0;
+    }
+    return -1;
+}
+
+} // namespace proj
+
+// DEMInterpolator.cpp:592-611: project to the raster's CRS, then interpolateXY.
 inline double dem_interp_lonlat(const I3B_DEM& d, double lon, double lat)
 {
     if (!d.have_raster) return d.ref_height;
-    const double x = lon * 180.0 / M_PI;
-    const double y = lat * 180.0 / M_PI;
+    double x, y;
+    if (proj::forward(d.epsg, lon, lat, &x, &y) != 0) return d.ref_height;
     return dem_interp_xy(d, x, y);
 }
 

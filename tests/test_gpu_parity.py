@@ -138,6 +138,20 @@ def test_raster_dem_doppler_lut_tsx(oracle):
     check(gpu, cpu, sc)
 
 
+@pytest.mark.parametrize("dem_epsg", ["utm", 3413, 6933])
+def test_raster_dem_in_projected_coordinates(oracle, dem_epsg):
+    """Raster DEM in UTM / polar stereographic / EASE-2 coordinates
+    (DEMInterpolator::interpolateLonLat -> createProj(epsg)->forward,
+    geometry/DEMInterpolator.cpp:592-611, core/Projections.cpp:373-402)."""
+    sc = synth.make_scene("c4", pulses=1024, bins=1024, out_lines=12, out_samples=140, n_targets=1,
+                          dem_epsg=dem_epsg)
+    assert sc.dem.have_raster and sc.dem.epsg_code != 4326
+    gpu = run_gpu(sc)
+    cpu = run_cpu(oracle, sc)
+    assert np.nanmax(cpu[2]) - np.nanmin(cpu[2]) > 1.0  # the height layer really varies
+    check(gpu, cpu, sc)
+
+
 @pytest.mark.parametrize("method", ["bilinear", "bicubic", "nearest"])
 def test_other_dem_interpolators(oracle, method):
     sc = synth.make_scene("c4", pulses=512, bins=1024, out_lines=8, out_samples=64, n_targets=1)

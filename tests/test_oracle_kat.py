@@ -297,3 +297,71 @@ def test_port_equals_reference_sources(oracles, name, kw):
     m = np.isfinite(b)
     assert np.linalg.norm((a - b)[m]) <= 1e-6 * np.linalg.norm(b[m])
     np.testing.assert_allclose(ha, hb, rtol=0, atol=1e-5)
+
+
+# ---- map projections of raster DEMs (core/Projections.cpp) ---------------------------------
+
+PROJ_POINTS = [(-118.3, 34.1), (11.2, -3.4), (-45.0, 72.0), (100.0, -75.0), (179.2, 60.0), (3.0, 0.0)]
+
+
+def _epsg_cases(lon_deg, lat_deg):
+    import math
+    from isce3_b200.projections import utm_epsg_for
+    return [utm_epsg_for(math.radians(lon_deg), math.radians(lat_deg)), 3413, 3031, 6933, 4326]
+
+
+def test_projection_known_answers(oracles):
+    """Textbook anchors: a point on a UTM central meridian at the equator maps to
+    (500000, 0) north / (500000, 10000000) south; the pole is the origin of the polar
+    stereographic grids; EASE-2 (6933) is linear in longitude."""
+    import math
+    for o in [o for o in oracles if o is not None]:
+        st, x, y = o.project_forward(32631, math.radians(3.0), 0.0)
+        assert st == 0 and abs(x - 500000.0) < 1e-6 and abs(y) < 1e-6
+        st, x, y = o.project_forward(32731, math.radians(3.0), 0.0)
+        assert st == 0 and abs(x - 500000.0) < 1e-6 and abs(y - 1.0e7) < 1e-6
+        st, x, y = o.project_forward(3413, 0.3, math.pi / 2)
+        assert st == 0 and abs(x) < 1e-6 and abs(y) < 1e-6
+        st, x1, _ = o.project_forward(6933, 0.5, 0.2)
+        st, x2, _ = o.project_forward(6933, 1.0, 0.2)
+        assert abs(x2 - 2 * x1) < 1e-6
+        # UTM refuses points a quarter of the globe away from the zone (Projections.cpp:199-212)
+        assert o.project_forward(32631, math.radians(3.0 + 89.9), 0.0)[0] == 1
+
+
+def test_projection_port_python_and_reference_agree(oracles):
+    """Restated forward projections (oracle port, host mirror isce3_b200.projections) against
+    the reference's own Projections.cpp (oracle/_ref) on scattered points."""
+    import math
+    from isce3_b200.projections import make_projection
+    for lon_d, lat_d in PROJ_POINTS:
+        lon, lat = math.radians(lon_d), math.radians(lat_d)
+        for epsg in _epsg_cases(lon_d, lat_d):
+            if epsg == 3413 and lat_d < -60 or epsg == 3031 and lat_d > 60:
+                continue
+            vals = [o.project_forward(epsg, lon, lat) for o in oracles if o is not None]
+            px, py = make_projection(epsg).forward(lon, lat)
+            for st, x, y in vals:
+                assert st == 0
+                assert abs(x - px) <= 1e-6 * max(1.0, abs(px)) and abs(y - py) <= 1e-6 * max(1.0, abs(py))
+            if len(vals) == 2:
+                assert abs(vals[0][1] - vals[1][1]) <= 1e-7 * max(1.0, abs(vals[1][1]))
+                assert abs(vals[0][2] - vals[1][2]) <= 1e-7 * max(1.0, abs(vals[1][2]))
+
+
+def test_projected_dem_sampling_matches_between_oracles(oracles):
+    """DEMInterpolator.interpolateLonLat on a UTM raster: port (restated projection + sampler)
+    vs reference projection + sampler."""
+    import math
+    from isce3_b200 import synth
+    from isce3_b200.projections import utm_epsg_for
+    lon, lat = math.radians(-118.3), math.radians(34.1)
+    dem = synth.synthetic_dem_projected(utm_epsg_for(lon, lat), lon, lat, 20e3, posting_m=100.0)
+    rng = np.random.default_rng(3)
+    for _ in range(50):
+        lo = lon + rng.uniform(-0.15, 0.15) * math.pi / 180
+        la = lat + rng.uniform(-0.15, 0.15) * math.pi / 180
+        h = [o.dem_interp(dem, lo, la) for o in oracles if o is not None]
+        assert 0.0 <= h[0] <= 2000.0
+        if len(h) == 2:
+            assert abs(h[0] - h[1]) <= 1e-4
