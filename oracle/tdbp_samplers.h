@@ -134,6 +134,31 @@ inline U nearest(double x, double y, const Grid2d<U>& z)
     return z((long) std::round(y), (long) std::round(x));
 }
 
+#ifdef TDBP_USE_REFERENCE_INTERPOLATORS
+} // namespace tdbp_oracle
+#include <isce3/core/Interpolator.h>
+namespace tdbp_oracle {
+// oracle/_ref build: the 2-D interpolation itself is the REFERENCE's
+// (core/{Bilinear,Bicubic,Spline2d,NearestNeighbor}Interpolator.cpp compiled unchanged; spline
+// order 6 as createInterpolator's default, core/Interpolator.h:203-221).  The restated
+// versions above are what the port oracle uses; tests compare the two builds.
+template<typename U>
+inline U interp2d(int method, double x, double y, const Grid2d<U>& z)
+{
+    using Map = Eigen::Map<const isce3::core::EArray2D<U>>;
+    const Map m(z.data, z.rows, z.cols);
+    static const isce3::core::BilinearInterpolator<U> bilinear_i;
+    static const isce3::core::BicubicInterpolator<U> bicubic_i;
+    static const isce3::core::Spline2dInterpolator<U> biquintic_i(6);
+    static const isce3::core::NearestNeighborInterpolator<U> nearest_i;
+    switch (method) {
+    case I3B_INTERP_BICUBIC: return bicubic_i.interpolate(x, y, m);
+    case I3B_INTERP_BIQUINTIC: return biquintic_i.interpolate(x, y, m);
+    case I3B_INTERP_NEAREST: return nearest_i.interpolate(x, y, m);
+    default: return bilinear_i.interpolate(x, y, m);
+    }
+}
+#else
 template<typename U>
 inline U interp2d(int method, double x, double y, const Grid2d<U>& z)
 {
@@ -144,6 +169,7 @@ inline U interp2d(int method, double x, double y, const Grid2d<U>& z)
     default: return bilinear<U>(x, y, z); // createInterpolator fallback
     }
 }
+#endif
 
 // LUT2d.h:84-95
 inline bool lut2d_contains(const I3B_LUT2d& l, double y, double x)
