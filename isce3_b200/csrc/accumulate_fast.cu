@@ -283,6 +283,38 @@ struct Weights {
                 t.o[m] = __int_as_float(__float_as_int(Coef::o(m, NO - 1)) + zero);
         }
     }
+    // One tap pair: wlo = w_m(f), whi = w_{K-1-m}(f) of both pixels, from h = f*f, nf = -f.
+    template<int m>
+    __device__ static __forceinline__ void pair(f32x2 f, f32x2 h, f32x2 nf, f32x2& wlo, f32x2& whi,
+                                                const Top& top)
+    {
+        float cev[4], cov[4];
+        if (Coef::kImm) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                cev[i] = Coef::e(m, i);
+                cov[i] = Coef::o(m, i);
+            }
+            if (kHoist) {
+                cev[NE - 1] = top.e[m];
+                cov[NO - 1] = top.o[m];
+            }
+        } else {
+            const float4 ce = *reinterpret_cast<const float4*>(c_poly[m].e);
+            const float4 co = *reinterpret_cast<const float4*>(c_poly[m].o);
+            cev[0] = ce.x; cev[1] = ce.y; cev[2] = ce.z; cev[3] = ce.w;
+            cov[0] = co.x; cov[1] = co.y; cov[2] = co.z; cov[3] = co.w;
+        }
+        f32x2 e = bcast2(cev[NE - 1]);
+#pragma unroll
+        for (int i = NE - 2; i >= 0; --i) e = fma2(e, h, bcast2(cev[i]));
+        f32x2 o = bcast2(cov[NO - 1]);
+#pragma unroll
+        for (int i = NO - 2; i >= 0; --i) o = fma2(o, h, bcast2(cov[i]));
+        wlo = fma2(f, o, e);
+        whi = fma2(nf, o, e);
+    }
+
     // Tap weights of TWO pixels at once: f = (f_pixel0, f_pixel1) in [-0.5, 0.5);
     // w[m] = (w_m(f0), w_m(f1)).  Coefficients enter as scalar-broadcast operands.
     __device__ static __forceinline__ void eval(f32x2 f, f32x2 (&w)[K], const Top& top)
@@ -432,6 +464,74 @@ __device__ __forceinline__ void mac_rotate(PairState& S, const f32x2 (&w)[K], co
     rotate_accumulate<EDGE>(S, a0, a1, cs0, sn0, cs1, sn1, in0, in1);
 }
 
+// Wide kernels (K = 16, 32): weights and window samples of all K taps do not fit the
+// register file next to each other, so the taps are processed in chunks of 4 tap PAIRS
+// (m, K-1-m share their even/odd polynomial parts): 8 weights, a 6-sample piece of the
+// window at each end, 16 MACs -- then the next chunk, moving inwards from both ends.  The
+// window pieces of consecutive chunks overlap by one LDS.128, which is carried in registers.
+template<int K, int D, class Coef, int OFF, int C = 0>
+struct ChunkedMac {
+    typedef Weights<K, D, Coef> WT;
+    __device__ static __forceinline__ void run(f32x2 f, f32x2 h, f32x2 nf, uint32_t src,
+                                               f32x2 (&lo)[6], f32x2 (&hi)[6], f32x2& a0, f32x2& a1,
+                                               const typename WT::Top& top)
+    {
+        constexpr int LO0 = 4 * C;         // first sample of the low piece  (even)
+        constexpr int HI0 = K - 4 * C - 4; // first sample of the high piece (even)
+        // low piece: samples [LO0, LO0 + 6); the first two came with the previous chunk
+        if (C == 0) {
+            const float4 v = lds128(src + 8u * LO0);
+            lo[0] = pack2(v.x, v.y);
+            lo[1] = pack2(v.z, v.w);
+        }
+        {
+            const float4 v = lds128(src + 8u * (LO0 + 2)), u = lds128(src + 8u * (LO0 + 4));
+            lo[2] = pack2(v.x, v.y);
+            lo[3] = pack2(v.z, v.w);
+            lo[4] = pack2(u.x, u.y);
+            lo[5] = pack2(u.z, u.w);
+        }
+        // high piece: samples [HI0, HI0 + 6); the last two came with the previous chunk
+        if (C == 0) {
+            const float4 v = lds128(src + 8u * (HI0 + 4));
+            hi[4] = pack2(v.x, v.y);
+            hi[5] = pack2(v.z, v.w);
+        }
+        {
+            const float4 v = lds128(src + 8u * HI0), u = lds128(src + 8u * (HI0 + 2));
+            hi[0] = pack2(v.x, v.y);
+            hi[1] = pack2(v.z, v.w);
+            hi[2] = pack2(u.x, u.y);
+            hi[3] = pack2(u.z, u.w);
+        }
+        f32x2 wl[4], wh[4];
+        WT::template pair<4 * C + 0>(f, h, nf, wl[0], wh[0], top);
+        WT::template pair<4 * C + 1>(f, h, nf, wl[1], wh[1], top);
+        WT::template pair<4 * C + 2>(f, h, nf, wl[2], wh[2], top);
+        WT::template pair<4 * C + 3>(f, h, nf, wl[3], wh[3], top);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float w0, w1;
+            // tap 4C+i sits at sample OFF + 4C + i of the window, i.e. lo[OFF + i]
+            unpack2(wl[i], w0, w1);
+            a0 = fma2(bcast2(w0), lo[OFF + i], a0);
+            a1 = fma2(bcast2(w1), lo[OFF + i + 1], a1);
+            // tap K-1-(4C+i) sits at sample OFF + K-1-4C-i, i.e. hi[OFF + 3 - i]
+            unpack2(wh[i], w0, w1);
+            a0 = fma2(bcast2(w0), hi[OFF + 3 - i], a0);
+            a1 = fma2(bcast2(w1), hi[OFF + 3 - i + 1], a1);
+        }
+        if constexpr (4 * (C + 1) < K / 2) {
+            // next chunk: low piece moves up by 4 samples, high piece down by 4
+            lo[0] = lo[4];
+            lo[1] = lo[5];
+            hi[4] = hi[0];
+            hi[5] = hi[1];
+            ChunkedMac<K, D, Coef, OFF, C + 1>::run(f, h, nf, src, lo, hi, a0, a1, top);
+        }
+    }
+};
+
 // One staged pulse tile (TK pulses) for the thread's pixel pair.  EDGE = false: every pixel
 // of the CTA integrates every pulse of the tile (no aperture test in the loop).
 //
@@ -450,7 +550,9 @@ __device__ __forceinline__ void tile_body(PairState& S, float& jf, unsigned& jjm
     WT::load_top(top, zero);
     const int iw0 = S.i0rel[0] - wlo, iw1 = S.i0rel[1] - wlo;
     uint32_t line_addr = lines_addr;
-#pragma unroll KK_UNROLL
+    // (wide kernels: the body is already hundreds of instructions per pulse)
+    constexpr int kUnroll = (K >= 16) ? 1 : KK_UNROLL;
+#pragma unroll kUnroll
     for (int kk = 0; kk < TK; ++kk) {
         // keep the staged line address a loop-carried register (ptxas otherwise rebuilds it
         // from the shared-memory base every pulse: ~10 instructions)
@@ -475,6 +577,18 @@ __device__ __forceinline__ void tile_body(PairState& S, float& jf, unsigned& jjm
         const bool in1 = !EDGE || krel1 + (unsigned) kk < (unsigned) S.kspan[1];
         sincos_fast(ang0, sn0, cs0);
         sincos_fast(ang1, sn1, cs1);
+        if constexpr (K >= 16 && K % 8 == 0) {
+            if (j1 == j0 + 1) {
+                const uint32_t src = line_addr + ((j0 >> 1) << 4);
+                const f32x2 h = mul2(f, f), nf = mul2(f, bcast2(-1.0f));
+                f32x2 lo[6], hi[6], a0 = 0ull, a1 = 0ull;
+                if (j0 & 1u) ChunkedMac<K, D, Coef, 1>::run(f, h, nf, src, lo, hi, a0, a1, top);
+                else ChunkedMac<K, D, Coef, 0>::run(f, h, nf, src, lo, hi, a0, a1, top);
+                rotate_accumulate<EDGE>(S, a0, a1, cs0, sn0, cs1, sn1, in0, in1);
+                line_addr += row_bytes;
+                continue;
+            }
+        }
         f32x2 w[K];
         if (j1 == j0 + 1) {
             // shared register window: K+1 samples (+1 when the start is odd); the loads are

@@ -1,3 +1,3 @@
-bash scripts/run_variants.sh 0.5 S64U2 S128U2 S64U4 > gpurun_out/variants.log 2>&1
-ISCE3_B200_LIB=isce3_b200/csrc/build/variants/lib_S64U2.so python scripts/gpu_quick.py > gpurun_out/quick_S64U2.log 2>&1
-ISCE3_B200_LIB=isce3_b200/csrc/build/variants/lib_S128U2.so python scripts/gpu_quick.py > gpurun_out/quick_S128U2.log 2>&1
+python scripts/gpu_quick.py > gpurun_out/quick.log 2>&1
+for k in 8 16 32; do python scripts/perf_fast.py 0.5 c5k$k $k c5; done > gpurun_out/perf.log 2>&1
+python scripts/perf_fast.py 0.5 c2k9 >> gpurun_out/perf.log 2>&1

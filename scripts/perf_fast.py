@@ -11,7 +11,11 @@ tag = sys.argv[2] if len(sys.argv) > 2 else ""
 kw = dict(pulses=16384, bins=int(12288 * scale), out_lines=int(8192 * scale), out_samples=int(8192 * scale), noise_db=False, n_targets=1)
 if len(sys.argv) > 3:
     kw["taps"] = int(sys.argv[3])
-sc = synth.make_scene("c2", **kw)
+name = sys.argv[4] if len(sys.argv) > 4 else "c2"
+if name == "c5":
+    kw = dict(pulses=16384, bins=4096, out_lines=int(2048 * scale), out_samples=2048, noise_db=False, n_targets=1,
+              taps=kw.get("taps", 16))
+sc = synth.make_scene(name, **kw)
 with BackprojectPlan(*sc.backproject_args()) as plan:
     plan.execute()
     ms = []
