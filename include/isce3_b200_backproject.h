@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define I3B_ABI_VERSION 1
+#define I3B_ABI_VERSION 2
 
 /* ---- status codes --------------------------------------------------------
  * 0..11 mirror isce3::error::ErrorCode (cxx/isce3/error/ErrorCode.h:8-21): they
@@ -208,6 +208,16 @@ typedef struct {
      * current device only (reference behaviour, focus.py:1589-1595).       */
     int32_t n_devices;
     const int32_t* devices;
+
+    /* output-encoding extension (ABI 2): what the workflow's writer does to every focused
+     * block on the host before storing it (nisar/workflows/focus.py:899-925), fused into
+     * the kernel that converts the accumulator to complex64.  Both optional.            */
+    const float* range_cor;  /* complex64 [out.width] or NULL: out[j][i] *= range_cor[i]
+                                (range deramp / scale phasors, focus.py:899-900)       */
+    int32_t mantissa_nbits;  /* 0: keep all 23 mantissa bits; 1..23: zero the least
+                                significant ones like truncate_mantissa(z, n)
+                                (python/packages/isce3/core/types.py:116-171)          */
+    int32_t _pad2;
 } I3B_BackprojectArgs;
 
 enum {

@@ -15,7 +15,7 @@ from pathlib import Path
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # status codes (include/isce3_b200_backproject.h)
 SUCCESS = 0
@@ -165,6 +165,9 @@ class BackprojectArgs(C.Structure):
         ("geo2rdr", Geo2RdrBracketParams),
         ("n_devices", C.c_int32),
         ("devices", C.POINTER(C.c_int32)),
+        ("range_cor", C.c_void_p),
+        ("mantissa_nbits", C.c_int32),
+        ("_pad2", C.c_int32),
     ]
 
 

@@ -196,7 +196,7 @@ static float elapsed(const Event& a, const Event& b)
 struct HostScene {
     I3B_BackprojectArgs a;
     std::vector<double> out_pos, out_vel, in_pos, in_vel, out_dop, in_dop;
-    std::vector<float> dem, kdata;
+    std::vector<float> dem, kdata, range_cor;
     std::vector<int> devices;
 };
 
@@ -237,6 +237,7 @@ static void validate(const I3B_BackprojectArgs& a)
         if (a.dem.method == I3B_INTERP_SINC) bad("sinc DEM interpolation is not supported");
     }
     if (!(a.fc > 0) || !(a.ds > 0)) bad("fc and ds must be positive");
+    if (a.mantissa_nbits < 0 || a.mantissa_nbits > 23) bad("mantissa_nbits must be in [0, 23]");
     const I3B_Kernel& k = a.kernel;
     switch (k.kind) {
     case I3B_KERNEL_BARTLETT:
@@ -314,7 +315,7 @@ struct Shard {
     DevBuf<PulseRec> pulse;
     DevBuf<PixelRec> pix;
     DevBuf<double2> acc;
-    DevBuf<float2> out, rc;
+    DevBuf<float2> out, rc, range_cor;
     DevBuf<DevStatus> status;
     DevBuf<TileInfo> tile_info;
     const float2* rc_dev = nullptr; // staged lines (or the caller's device pointer)
@@ -373,6 +374,7 @@ static void shard_setup(const HostScene& hs, Shard& sh)
     if (ig.doppler.have_data) sh.in_dop.upload(ig.doppler.data, (size_t) ig.doppler.length * ig.doppler.width, s);
     if (a.dem.have_raster) sh.dem.upload(a.dem.data, (size_t) a.dem.length * a.dem.width, s);
     if (a.kernel.data && a.kernel.n > 0) sh.kdata.upload(a.kernel.data, (size_t) a.kernel.n, s);
+    if (a.range_cor) sh.range_cor.upload(reinterpret_cast<const float2*>(a.range_cor), (size_t) og.grid.width, s);
 
     auto dev_orbit = [](const I3B_Orbit& o, const double* p, const double* v) {
         return DevOrbit {o.t0, o.dt, o.n, o.method, p, v};
@@ -596,7 +598,7 @@ static void shard_run(const HostScene& hs, Shard& sh, bool resident_only)
         return;
     }
     if (sh.ap.npix > 0) {
-        launch_finalize(sh.ap.npix, sh.pix.p, sh.acc.p, sh.out.p, s);
+        launch_finalize(sh.ap.npix, sh.ap.out_width, sh.pix.p, sh.acc.p, sh.out.p, sh.range_cor.p, hs.a.mantissa_nbits, s);
         CK(cudaGetLastError());
         sh.stats.total_launches += 1;
     }
@@ -618,7 +620,7 @@ static void shard_run(const HostScene& hs, Shard& sh, bool resident_only)
         eb0.record(s);
         shard_accumulate(sh, kfirst, klast, s);
         eb1.record(s);
-        launch_finalize(sh.ap.npix, sh.pix.p, sh.acc.p, sh.out.p, s);
+        launch_finalize(sh.ap.npix, sh.ap.out_width, sh.pix.p, sh.acc.p, sh.out.p, sh.range_cor.p, hs.a.mantissa_nbits, s);
         CK(cudaStreamSynchronize(s));
         sh.stats.ms_accumulate += elapsed(eb0, eb1);
         sh.stats.used_fast_kernel = 0;
@@ -664,6 +666,10 @@ static std::unique_ptr<I3B_Plan> make_plan(const I3B_BackprojectArgs* args)
     if (args->kernel.data && args->kernel.n > 0) {
         hs.kdata.assign(args->kernel.data, args->kernel.data + args->kernel.n);
         hs.a.kernel.data = hs.kdata.data();
+    }
+    if (args->range_cor) {
+        hs.range_cor.assign(args->range_cor, args->range_cor + 2 * (size_t) args->out_geometry.grid.width);
+        hs.a.range_cor = hs.range_cor.data();
     }
     int ndev_avail = 0;
     {

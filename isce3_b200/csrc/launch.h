@@ -52,8 +52,8 @@ void launch_target_solve(const SolveParams& P, PixelRec* pix, float* height, Til
                          int n_tiles, DevStatus* status, cudaStream_t s);
 void launch_accumulate_generic(const AccumParams& P, const PixelRec* pix, const double* pv,
                                const float2* rc, double2* acc, cudaStream_t s);
-void launch_finalize(long long npix, const PixelRec* pix, const double2* acc, float2* out,
-                     cudaStream_t s);
+void launch_finalize(long long npix, int out_width, const PixelRec* pix, const double2* acc, float2* out,
+                     const float2* range_cor, int mantissa_nbits, cudaStream_t s);
 
 // fast path (accumulate_fast.cu)
 // `host_kernel`: same kernel with its data pointer in HOST memory (polynomial fitting).

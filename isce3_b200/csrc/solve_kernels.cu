@@ -205,8 +205,12 @@ accumulate_generic_kernel(AccumParams P, const PixelRec* __restrict__ pix,
 }
 
 // ---- finalisation: complex<double> accumulator -> complex64, NaN for failed pixels ---
-__global__ void finalize_kernel(long long npix, const PixelRec* __restrict__ pix,
-                                const double2* __restrict__ acc, float2* __restrict__ out)
+// Optional output encoding of the workflow's writer fused in (focus.py:899-925): multiply
+// every range column by a complex phasor (deramp / scale), zero the low mantissa bits
+// (isce3/core/types.py:116-171).
+__global__ void finalize_kernel(long long npix, int out_width, const PixelRec* __restrict__ pix,
+                                const double2* __restrict__ acc, float2* __restrict__ out,
+                                const float2* __restrict__ range_cor, unsigned mantissa_mask)
 {
     const long long tid = (long long) blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= npix) return;
@@ -217,6 +221,16 @@ __global__ void finalize_kernel(long long npix, const PixelRec* __restrict__ pix
         const double2 a = acc[tid];
         o.x = (float) a.x;
         o.y = (float) a.y;
+        if (range_cor) {
+            // complex64 * complex64 in float, products rounded separately like the host's
+            const float2 c = range_cor[tid % out_width];
+            const float re = __fsub_rn(__fmul_rn(o.x, c.x), __fmul_rn(o.y, c.y));
+            const float im = __fadd_rn(__fmul_rn(o.x, c.y), __fmul_rn(o.y, c.x));
+            o.x = re;
+            o.y = im;
+        }
+        o.x = __uint_as_float(__float_as_uint(o.x) & mantissa_mask);
+        o.y = __uint_as_float(__float_as_uint(o.y) & mantissa_mask);
     }
     out[tid] = o;
 }
@@ -247,11 +261,13 @@ void launch_accumulate_generic(const AccumParams& P, const PixelRec* pix, const 
     accumulate_generic_kernel<<<grid, 256, 0, s>>>(P, pix, pv, rc, acc);
 }
 
-void launch_finalize(long long npix, const PixelRec* pix, const double2* acc, float2* out,
-                     cudaStream_t s)
+void launch_finalize(long long npix, int out_width, const PixelRec* pix, const double2* acc, float2* out,
+                     const float2* range_cor, int mantissa_nbits, cudaStream_t s)
 {
     const unsigned grid = (unsigned) ((npix + 255) / 256);
-    finalize_kernel<<<grid, 256, 0, s>>>(npix, pix, acc, out);
+    const unsigned mask = (mantissa_nbits > 0 && mantissa_nbits < 23) ? (0xFFFFFFFFu << (23 - mantissa_nbits))
+                                                                      : 0xFFFFFFFFu;
+    finalize_kernel<<<grid, 256, 0, s>>>(npix, out_width, pix, acc, out, range_cor, mask);
 }
 
 } // namespace i3b

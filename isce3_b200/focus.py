@@ -79,7 +79,8 @@ def _check_array(a, name, dtype, shape, what):
 
 def build_args(out, out_geometry, in_, in_geometry, dem, fc, ds, kernel,
                dry_tropo_model="tsx", rdr2geo_params=None, geo2rdr_params=None, batch=1024,
-               height=None, devices=None, force_generic=False) -> Flattened:
+               height=None, devices=None, force_generic=False, range_cor=None,
+               mantissa_nbits=None) -> Flattened:
     """Validate like the reference binding and flatten into an I3B_BackprojectArgs."""
     oshape = (out_geometry.grid_length, out_geometry.grid_width)
     ishape = (in_geometry.grid_length, in_geometry.grid_width)
@@ -117,6 +118,15 @@ def build_args(out, out_geometry, in_, in_geometry, dem, fc, ds, kernel,
     a.dry_tropo_model = atm
     a.batch = int(batch)
     a.rdr2geo, a.geo2rdr = r2g, g2r
+    if range_cor is not None:
+        rcor = fl.hold(range_cor, np.complex64)
+        if rcor.shape != (oshape[1],):
+            raise InvalidArgument("range_cor length must match the output radar grid width")
+        a.range_cor = rcor.ctypes.data
+    if mantissa_nbits is not None:
+        if not 0 < int(mantissa_nbits) <= 23:  # isce3/core/types.py:147-151
+            raise InvalidArgument(f"Require 0 < significant_bits={mantissa_nbits} <= 23")
+        a.mantissa_nbits = int(mantissa_nbits) % 23  # 23 keeps every bit
     if devices:
         dev = np.ascontiguousarray(devices, dtype=np.int32)
         fl.keep.append(dev)
@@ -149,16 +159,22 @@ def last_stats() -> dict:
 
 def backproject(out, out_geometry, in_, in_geometry, dem, fc, ds, kernel,
                 dry_tropo_model="tsx", rdr2geo_params=None, geo2rdr_params=None, batch=1024,
-                height=None, *, devices=None, force_generic=False) -> bool:
+                height=None, *, devices=None, force_generic=False, range_cor=None,
+                mantissa_nbits=None) -> bool:
     """Focus in azimuth via time-domain backprojection on B200.
 
     Same positional arguments, defaults and return value as
     ``isce3.cuda.focus.backproject`` (returns True when any pixel's geometry failed
     to converge; those pixels are NaN).  ``devices`` (keyword-only extension) lists
-    CUDA device ordinals to shard the output grid over by azimuth block.
+    CUDA device ordinals to shard the output grid over by azimuth block.  ``range_cor``
+    (complex64 per output range column) and ``mantissa_nbits`` (keyword-only extensions) fuse
+    what the workflow's writer does to each block on the host -- ``z *= range_cor`` and
+    ``truncate_mantissa(z, n)`` (nisar/workflows/focus.py:899-925) -- into the device pass
+    that produces ``out``.
     """
     fl = build_args(out, out_geometry, in_, in_geometry, dem, fc, ds, kernel, dry_tropo_model,
-                    rdr2geo_params, geo2rdr_params, batch, height, devices, force_generic)
+                    rdr2geo_params, geo2rdr_params, batch, height, devices, force_generic,
+                    range_cor, mantissa_nbits)
     if out is None:
         raise TypeError("output array is required")
     lib = _capi.load_library()

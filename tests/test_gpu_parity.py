@@ -242,6 +242,34 @@ def test_non_finite_samples_only_poison_the_apertures_that_hold_them(oracle):
     check(gpu, cpu)
 
 
+def test_fused_output_encoding_matches_the_workflow_writer():
+    """range_cor / mantissa_nbits extensions: same result as the host post-processing of
+    BackgroundWriter.write (nisar/workflows/focus.py:899-925): z *= range_cor[None, :], then
+    truncate_mantissa(z, nbits) (isce3/core/types.py:116-171)."""
+    sc = synth.make_scene("c2", pulses=2048, bins=1024, out_lines=16, out_samples=200, n_targets=1)
+    _, plain, _, _ = run_gpu(sc)
+    rng = np.random.default_rng(11)
+    cor = (2.5 * np.exp(2j * np.pi * rng.uniform(size=200))).astype(np.complex64)
+    out = np.zeros(shape_of(sc), np.complex64)
+    backproject(out, *sc.backproject_args(), range_cor=cor)
+    want = plain * cor[None, :]
+    assert np.max(np.abs(out - want)) <= 4e-7 * np.max(np.abs(want))
+    nbits = 10
+    backproject(out, *sc.backproject_args(), range_cor=cor, mantissa_nbits=nbits)
+    mask = np.uint32((0xFFFFFFFF << (23 - nbits)) & 0xFFFFFFFF)
+    bits = out.view(np.uint32)
+    assert np.all(bits & ~mask == 0), "low mantissa bits must be zero"
+    trunc = want.copy()
+    trunc.view(np.uint32)[...] &= mask
+    # identical except where the fused multiply rounded the last kept bit differently
+    assert np.max(np.abs(out - trunc)) <= 2.0 ** -nbits * np.max(np.abs(want))
+    assert np.mean(out == trunc) > 0.99
+    with pytest.raises(focus.InvalidArgument):
+        backproject(out, *sc.backproject_args(), range_cor=cor[:-1])
+    with pytest.raises(focus.InvalidArgument):
+        backproject(out, *sc.backproject_args(), mantissa_nbits=24)
+
+
 def test_failed_pixels_are_nan_and_flagged(oracle):
     """geo2rdr bracket that excludes part of the image: those pixels are (NaN, NaN), the call
     returns True (FailedToConverge); rdr2geo failure also NaNs the height layer."""
