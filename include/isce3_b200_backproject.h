@@ -60,8 +60,10 @@ enum {
     I3B_EXC_OVERFLOW_ERROR = -4,   /* isce3::except::OverflowError          */
     I3B_EXC_OUT_OF_RANGE = -5,     /* isce3::except::OutOfRange (orbit)     */
     I3B_EXC_CUDA_ERROR = -6,       /* isce3::cuda::except::CudaError        */
-    I3B_EXC_NO_DEVICE = -7         /* no usable sm_100 device: there is NO
+    I3B_EXC_NO_DEVICE = -7,        /* no usable sm_100 device: there is NO
                                       CPU fallback in this library          */
+    I3B_EXC_LENGTH_ERROR = -8      /* isce3::except::LengthError (RangeComp
+                                      batch > maxbatch)                     */
 };
 
 /* isce3::core::LookSide (cxx/isce3/core/LookSide.h:13-17) */
@@ -308,6 +310,29 @@ int i3b_measure_peaks(int device, I3B_Peaks* peaks);
 int i3b_release_device_memory(void);
 /* Host-only diagnostic: the polynomial fit the fast kernel would use.      */
 int i3b_fit_tap_polynomials(const I3B_Kernel* kernel, I3B_TapPolyFit* fit);
+
+/* ---- range compression (the step that produces `in`) ---------
+ * isce3::focus::RangeComp (cxx/isce3/focus/RangeComp.h:13-116, RangeComp.cpp):
+ * frequency-domain convolution of each input line with the time-reversed complex
+ * conjugate of the chirp.  The reference has no CUDA twin of this class; the FFTs
+ * here are cuFFT.                                                              */
+enum { I3B_RANGECOMP_FULL = 0, I3B_RANGECOMP_VALID = 1, I3B_RANGECOMP_SAME = 2 }; /* RangeComp::Mode */
+typedef struct I3B_RangeComp I3B_RangeComp;
+/* RangeComp::RangeComp(chirp, inputsize, maxbatch, mode); chirp = complex64[chirp_size] */
+int i3b_rangecomp_create(const float* chirp, int chirp_size, int input_size, int max_batch,
+                         int mode, I3B_RangeComp** rc);
+/* fftSize(), outputSize(), firstValidSample() */
+int i3b_rangecomp_query(const I3B_RangeComp* rc, int* fft_size, int* output_size,
+                        int* first_valid_sample);
+/* RangeComp::rangecompress(out, in, batch): in complex64 [batch][input_size] ->
+ * out complex64 [batch][output_size]; host pointers, or device pointers on the
+ * current device with I3B_FLAG_DEVICE_POINTERS (output stays in HBM for a
+ * following i3b_backproject with the same flag).                              */
+int i3b_rangecomp_execute(I3B_RangeComp* rc, float* out, const float* in, int batch,
+                          uint32_t flags);
+double i3b_rangecomp_last_device_ms(const I3B_RangeComp* rc);
+const char* i3b_rangecomp_last_error(void);
+int i3b_rangecomp_destroy(I3B_RangeComp* rc);
 
 #ifdef __cplusplus
 }

@@ -29,6 +29,7 @@ EXC_OVERFLOW_ERROR = -4
 EXC_OUT_OF_RANGE = -5
 EXC_CUDA_ERROR = -6
 EXC_NO_DEVICE = -7
+EXC_LENGTH_ERROR = -8
 
 ERROR_STRINGS = {
     0: "Success",
@@ -240,6 +241,12 @@ EXPORTED_SYMBOLS = (
     "i3b_measure_peaks",
     "i3b_fit_tap_polynomials",
     "i3b_release_device_memory",
+    "i3b_rangecomp_create",
+    "i3b_rangecomp_query",
+    "i3b_rangecomp_execute",
+    "i3b_rangecomp_last_device_ms",
+    "i3b_rangecomp_last_error",
+    "i3b_rangecomp_destroy",
 )
 
 LIB_NAME = "libisce3_b200_backproject.so"
@@ -281,6 +288,17 @@ def load_library() -> C.CDLL:
     lib.i3b_fit_tap_polynomials.argtypes = [C.POINTER(Kernel), C.POINTER(TapPolyFit)]
     lib.i3b_fit_tap_polynomials.restype = C.c_int
     lib.i3b_release_device_memory.restype = C.c_int
+    lib.i3b_rangecomp_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    lib.i3b_rangecomp_create.restype = C.c_int
+    lib.i3b_rangecomp_query.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.i3b_rangecomp_query.restype = C.c_int
+    lib.i3b_rangecomp_execute.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32]
+    lib.i3b_rangecomp_execute.restype = C.c_int
+    lib.i3b_rangecomp_last_device_ms.argtypes = [C.c_void_p]
+    lib.i3b_rangecomp_last_device_ms.restype = C.c_double
+    lib.i3b_rangecomp_last_error.restype = C.c_char_p
+    lib.i3b_rangecomp_destroy.argtypes = [C.c_void_p]
+    lib.i3b_rangecomp_destroy.restype = C.c_int
     _lib = lib
     return lib
 

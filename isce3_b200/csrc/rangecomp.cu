@@ -1,0 +1,283 @@
+// Range compression on the GPU: the step that produces the backprojection's input
+// (SURVEY.md 8f rank 1).  Behavioural reference: isce3::focus::RangeComp,
+// cxx/isce3/focus/RangeComp.cpp:10-132 (matched filter = time-reversed conjugate chirp,
+// zero-pad to nextFastPower(chirp + input - 1), FFT, multiply, inverse FFT, crop by mode),
+// nextFastPower cxx/isce3/fft/FFTUtil.icc:39-75.  The FFTs are cuFFT (library code, batched
+// C2C); padding, spectrum multiply (with the 1/N scale folded into the reference spectrum)
+// and cropping are the kernels below.  All of it is HBM-bound streaming.
+#include <cuda_runtime.h>
+#include <cufft.h>
+
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/isce3_b200_backproject.h"
+
+namespace i3b {
+
+struct RcError : std::runtime_error {
+    int code;
+    RcError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define RC_CK(call)                                                                            \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            throw RcError(e__ == cudaErrorNoDevice ? I3B_EXC_NO_DEVICE : I3B_EXC_CUDA_ERROR,   \
+                          std::string(#call) + " failed: " + cudaGetErrorString(e__));         \
+    } while (0)
+#define RC_FFT(call)                                                                           \
+    do {                                                                                       \
+        cufftResult r__ = (call);                                                              \
+        if (r__ != CUFFT_SUCCESS)                                                              \
+            throw RcError(I3B_EXC_CUDA_ERROR, std::string(#call) + " failed: cufft status " +  \
+                                                      std::to_string((int) r__));              \
+    } while (0)
+
+// smallest m = 2^a 3^b 5^c >= n  (FFTUtil.icc:39-75)
+static int next_fast_power(int n)
+{
+    if (n <= 1) return 1;
+    const double logn = std::log((double) n);
+    const int max5 = (int) std::ceil(logn / std::log(5.0)), max3 = (int) std::ceil(logn / std::log(3.0));
+    long long best = INT32_MAX;
+    long long n5 = 1;
+    for (int x5 = 0; x5 <= max5; ++x5, n5 *= 5) {
+        long long n3 = 1;
+        for (int x3 = 0; x3 <= max3; ++x3, n3 *= 3) {
+            long long m = n5 * n3;
+            while (m < n) m *= 2;
+            best = std::min(best, m);
+        }
+    }
+    return (int) best;
+}
+
+static int output_size(int m, int n, int mode)
+{
+    switch (mode) {
+    case I3B_RANGECOMP_FULL: return m + n - 1;
+    case I3B_RANGECOMP_VALID: return std::max(m, n) - std::min(m, n) + 1;
+    default: return n;
+    }
+}
+
+// work[b][i] = in[b][i] for i < n_in, 0 up to nfft  (RangeComp.cpp:98-106)
+__global__ void rc_pad_kernel(float2* __restrict__ work, const float2* __restrict__ in, int n_in, int nfft,
+                              long long total)
+{
+    for (long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long) gridDim.x * blockDim.x) {
+        const long long b = t / nfft;
+        const int i = (int) (t - b * nfft);
+        work[t] = i < n_in ? in[b * n_in + i] : make_float2(0.f, 0.f);
+    }
+}
+
+// work[b][i] *= ref[i]   (ref already carries 1/nfft; RangeComp.cpp:109-116)
+__global__ void rc_multiply_kernel(float2* __restrict__ work, const float2* __restrict__ ref, int nfft,
+                                   long long total)
+{
+    for (long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long) gridDim.x * blockDim.x) {
+        const float2 r = ref[(int) (t % nfft)], w = work[t];
+        work[t] = make_float2(w.x * r.x - w.y * r.y, w.x * r.y + w.y * r.x);
+    }
+}
+
+// out[b][j] = work[b][offset + j]   (RangeComp.cpp:120-129)
+__global__ void rc_crop_kernel(float2* __restrict__ out, const float2* __restrict__ work, int n_out, int nfft,
+                               int offset, long long total)
+{
+    for (long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long) gridDim.x * blockDim.x) {
+        const long long b = t / n_out;
+        const int j = (int) (t - b * n_out);
+        out[t] = work[b * nfft + offset + j];
+    }
+}
+
+} // namespace i3b
+
+using namespace i3b;
+
+struct I3B_RangeComp {
+    int chirp_size = 0, input_size = 0, fft_size = 0, max_batch = 0, mode = 0, out_size = 0;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    float2 *d_ref = nullptr, *d_work = nullptr, *d_in = nullptr, *d_out = nullptr;
+    std::map<int, cufftHandle> plans; // by batch size
+    double ms_last = 0.0;
+
+    cufftHandle plan_for(int batch)
+    {
+        auto it = plans.find(batch);
+        if (it != plans.end()) return it->second;
+        cufftHandle h;
+        int n[1] = {fft_size};
+        RC_FFT(cufftPlanMany(&h, 1, n, nullptr, 1, fft_size, nullptr, 1, fft_size, CUFFT_C2C, batch));
+        RC_FFT(cufftSetStream(h, stream));
+        plans[batch] = h;
+        return h;
+    }
+    ~I3B_RangeComp()
+    {
+        cudaSetDevice(device);
+        for (auto& kv : plans) cufftDestroy(kv.second);
+        cudaFree(d_ref);
+        cudaFree(d_work);
+        cudaFree(d_in);
+        cudaFree(d_out);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+static thread_local std::string g_rc_error;
+
+template<class F>
+static int rc_guarded(F&& f)
+{
+    try {
+        return f();
+    } catch (const RcError& e) {
+        g_rc_error = e.what();
+        return e.code;
+    } catch (const std::exception& e) {
+        g_rc_error = e.what();
+        return I3B_EXC_RUNTIME_ERROR;
+    }
+}
+
+static unsigned grid_for(long long total) { return (unsigned) std::min<long long>((total + 255) / 256, 148 * 16); }
+
+extern "C" {
+
+const char* i3b_rangecomp_last_error(void) { return g_rc_error.c_str(); }
+
+int i3b_rangecomp_create(const float* chirp, int chirp_size, int input_size, int max_batch, int mode,
+                         I3B_RangeComp** out)
+{
+    return rc_guarded([&]() {
+        if (!out) throw RcError(I3B_EXC_INVALID_ARGUMENT, "null handle pointer");
+        *out = nullptr;
+        if (!chirp || chirp_size < 1) throw RcError(I3B_EXC_INVALID_ARGUMENT, "chirp is empty");
+        if (input_size < 1) throw RcError(I3B_EXC_DOMAIN_ERROR, "number of samples must be > 0");
+        if (max_batch < 1) throw RcError(I3B_EXC_DOMAIN_ERROR, "max batch size must be > 0");
+        if (mode < I3B_RANGECOMP_FULL || mode > I3B_RANGECOMP_SAME)
+            throw RcError(I3B_EXC_RUNTIME_ERROR, "unexpected range compression mode");
+        if ((long long) chirp_size + input_size - 1 > (1LL << 30))
+            throw RcError(I3B_EXC_OVERFLOW_ERROR, "convolution length exceeds the supported FFT size");
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+            throw RcError(I3B_EXC_NO_DEVICE, "no CUDA device available; isce3_b200 has no CPU fallback");
+        std::unique_ptr<I3B_RangeComp> rc(new I3B_RangeComp());
+        RC_CK(cudaGetDevice(&rc->device));
+        rc->chirp_size = chirp_size;
+        rc->input_size = input_size;
+        rc->max_batch = max_batch;
+        rc->mode = mode;
+        rc->fft_size = next_fast_power(output_size(chirp_size, input_size, I3B_RANGECOMP_FULL));
+        rc->out_size = output_size(chirp_size, input_size, mode);
+        RC_CK(cudaStreamCreateWithFlags(&rc->stream, cudaStreamNonBlocking));
+        const size_t nfft = (size_t) rc->fft_size;
+        RC_CK(cudaMalloc(&rc->d_ref, nfft * sizeof(float2)));
+        RC_CK(cudaMalloc(&rc->d_work, nfft * max_batch * sizeof(float2)));
+        RC_CK(cudaMalloc(&rc->d_in, (size_t) input_size * max_batch * sizeof(float2)));
+        RC_CK(cudaMalloc(&rc->d_out, (size_t) rc->out_size * max_batch * sizeof(float2)));
+        // matched filter: time-reversed complex conjugate of the chirp, zero-padded, in the
+        // frequency domain, times 1/nfft  (RangeComp.cpp:24-39,108)
+        std::vector<float2> ref(nfft, make_float2(0.f, 0.f));
+        for (int i = 0; i < chirp_size; ++i) {
+            const int s = chirp_size - 1 - i;
+            ref[i] = make_float2(chirp[2 * s], -chirp[2 * s + 1]);
+        }
+        RC_CK(cudaMemcpyAsync(rc->d_ref, ref.data(), nfft * sizeof(float2), cudaMemcpyHostToDevice, rc->stream));
+        cufftHandle one = rc->plan_for(1);
+        RC_FFT(cufftExecC2C(one, rc->d_ref, rc->d_ref, CUFFT_FORWARD));
+        RC_CK(cudaStreamSynchronize(rc->stream));
+        RC_CK(cudaMemcpy(ref.data(), rc->d_ref, nfft * sizeof(float2), cudaMemcpyDeviceToHost));
+        const float scale = (float) (1.0 / (double) nfft);
+        for (auto& z : ref) {
+            z.x *= scale;
+            z.y *= scale;
+        }
+        RC_CK(cudaMemcpy(rc->d_ref, ref.data(), nfft * sizeof(float2), cudaMemcpyHostToDevice));
+        *out = rc.release();
+        return 0;
+    });
+}
+
+int i3b_rangecomp_query(const I3B_RangeComp* rc, int* fft_size, int* out_size, int* first_valid_sample)
+{
+    if (!rc) return I3B_EXC_INVALID_ARGUMENT;
+    if (fft_size) *fft_size = rc->fft_size;
+    if (out_size) *out_size = rc->out_size;
+    if (first_valid_sample)
+        *first_valid_sample = rc->mode == I3B_RANGECOMP_FULL ? rc->chirp_size - 1
+                              : rc->mode == I3B_RANGECOMP_VALID ? 0 : rc->chirp_size / 2;
+    return 0;
+}
+
+int i3b_rangecomp_execute(I3B_RangeComp* rc, float* out, const float* in, int batch, uint32_t flags)
+{
+    return rc_guarded([&]() {
+        if (!rc || !out || !in) throw RcError(I3B_EXC_INVALID_ARGUMENT, "null argument");
+        if (batch > rc->max_batch) throw RcError(I3B_EXC_LENGTH_ERROR, "batch size exceeds max batch");
+        if (batch < 1) return 0;
+        RC_CK(cudaSetDevice(rc->device));
+        cudaStream_t s = rc->stream;
+        const bool dev = (flags & I3B_FLAG_DEVICE_POINTERS) != 0;
+        const int n_in = rc->input_size, n_out = rc->out_size, nfft = rc->fft_size;
+        const float2* d_in = reinterpret_cast<const float2*>(in);
+        float2* d_out = reinterpret_cast<float2*>(out);
+        cudaEvent_t e0, e1;
+        RC_CK(cudaEventCreate(&e0));
+        RC_CK(cudaEventCreate(&e1));
+        if (!dev) {
+            RC_CK(cudaMemcpyAsync(rc->d_in, in, (size_t) batch * n_in * sizeof(float2), cudaMemcpyHostToDevice, s));
+            d_in = rc->d_in;
+            d_out = rc->d_out;
+        }
+        RC_CK(cudaEventRecord(e0, s));
+        const long long tot = (long long) batch * nfft;
+        rc_pad_kernel<<<grid_for(tot), 256, 0, s>>>(rc->d_work, d_in, n_in, nfft, tot);
+        cufftHandle plan = rc->plan_for(batch);
+        RC_FFT(cufftExecC2C(plan, rc->d_work, rc->d_work, CUFFT_FORWARD));
+        rc_multiply_kernel<<<grid_for(tot), 256, 0, s>>>(rc->d_work, rc->d_ref, nfft, tot);
+        RC_FFT(cufftExecC2C(plan, rc->d_work, rc->d_work, CUFFT_INVERSE));
+        const int offset = rc->mode == I3B_RANGECOMP_FULL ? 0
+                           : rc->mode == I3B_RANGECOMP_VALID ? rc->chirp_size - 1 : rc->chirp_size / 2;
+        // NOTE Valid mode with chirp longer than input: offset follows the reference literally
+        const long long tout = (long long) batch * n_out;
+        rc_crop_kernel<<<grid_for(tout), 256, 0, s>>>(d_out, rc->d_work, n_out, nfft, offset, tout);
+        RC_CK(cudaGetLastError());
+        RC_CK(cudaEventRecord(e1, s));
+        if (!dev)
+            RC_CK(cudaMemcpyAsync(out, rc->d_out, (size_t) batch * n_out * sizeof(float2), cudaMemcpyDeviceToHost, s));
+        RC_CK(cudaStreamSynchronize(s));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        rc->ms_last = ms;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        return 0;
+    });
+}
+
+double i3b_rangecomp_last_device_ms(const I3B_RangeComp* rc) { return rc ? rc->ms_last : 0.0; }
+
+int i3b_rangecomp_destroy(I3B_RangeComp* rc)
+{
+    delete rc;
+    return 0;
+}
+
+} // extern "C"

@@ -23,4 +23,7 @@ focus = _types.SimpleNamespace(
     backproject=lambda out, out_geometry, in_, in_geometry, dem, fc, ds, kernel,
     dry_tropo_model="tsx", rdr2geo_params=None, geo2rdr_params=None, height=None:
     _focus.backproject(out, out_geometry, in_, in_geometry, dem, fc, ds, kernel,
-                       dry_tropo_model, rdr2geo_params, geo2rdr_params, 1024, height))
+                       dry_tropo_model, rdr2geo_params, geo2rdr_params, 1024, height),
+    # pybind_isce3/focus/focus.cpp: RangeComp, form_linear_chirp
+    RangeComp=_focus.RangeComp,
+    form_linear_chirp=_focus.form_linear_chirp)

@@ -251,3 +251,100 @@ def measure_peaks(device=0) -> dict:
     if status < 0:
         raise_for_status(status, (lib.i3b_last_error() or b"").decode())
     return pk.as_dict()
+
+
+# ---- range compression (isce3.focus.RangeComp, form_linear_chirp) ------------------------------
+
+import enum  # noqa: E402
+
+
+def form_linear_chirp(chirprate, duration, samplerate, centerfreq=0.0, amplitude=1.0, phi=0.0):
+    """isce3.focus.form_linear_chirp (cxx/isce3/focus/Chirp.cpp:10-58): complex64 LFM replica,
+    odd number of samples centred on t = 0."""
+    if duration <= 0.0:
+        raise DomainError("chirp duration must be > 0")
+    if samplerate <= 0.0:
+        raise DomainError("sampling rate must be > 0")
+    if amplitude <= 0.0:
+        raise DomainError("amplitude must be > 0")
+    size = int(math.floor(samplerate * duration + 1))
+    if size % 2 == 0:
+        size += 1
+    spacing = 1.0 / samplerate
+    tau = -0.5 * (size - 1) * spacing + spacing * np.arange(size)
+    phase = phi + 2.0 * np.pi * (centerfreq + 0.5 * chirprate * tau) * tau
+    return (amplitude * np.exp(1j * phase)).astype(np.complex64)
+
+
+class RangeComp:
+    """``isce3.focus.RangeComp`` on the GPU (python/extensions/pybind_isce3/focus/RangeComp.cpp:
+    same constructor, ``rangecompress(out, in)``, read-only properties and length checks).  The
+    reference has no CUDA twin of this class; see csrc/rangecomp.cu."""
+
+    class Mode(enum.IntEnum):
+        Full = 0
+        Valid = 1
+        Same = 2
+
+    def __init__(self, chirp, inputsize, maxbatch=1, mode=Mode.Full):
+        self._lib = _capi.load_library()
+        self._chirp = np.ascontiguousarray(chirp, dtype=np.complex64).ravel()
+        self._handle = C.c_void_p()
+        self._mode = RangeComp.Mode(int(mode))
+        status = self._lib.i3b_rangecomp_create(self._chirp.ctypes.data, self._chirp.size, int(inputsize),
+                                                int(maxbatch), int(self._mode), C.byref(self._handle))
+        self._check(status)
+        self._input_size, self._maxbatch = int(inputsize), int(maxbatch)
+        nfft, nout, first = C.c_int(), C.c_int(), C.c_int()
+        self._lib.i3b_rangecomp_query(self._handle, C.byref(nfft), C.byref(nout), C.byref(first))
+        self._fft_size, self._output_size, self._first = nfft.value, nout.value, first.value
+
+    def _check(self, status):
+        if status < 0:
+            msg = (self._lib.i3b_rangecomp_last_error() or b"").decode()
+            if status == _capi.EXC_LENGTH_ERROR:
+                raise ValueError(msg)  # std::length_error -> ValueError in pybind11
+            raise_for_status(status, msg)
+
+    chirp_size = property(lambda self: self._chirp.size)
+    input_size = property(lambda self: self._input_size)
+    fft_size = property(lambda self: self._fft_size)
+    maxbatch = property(lambda self: self._maxbatch)
+    mode = property(lambda self: self._mode)
+    output_size = property(lambda self: self._output_size)
+    first_valid_sample = property(lambda self: self._first)
+
+    def rangecompress(self, out, in_):
+        for a, name in ((out, "out"), (in_, "in")):
+            if not isinstance(a, np.ndarray) or a.dtype != np.complex64 or not a.flags.c_contiguous:
+                raise TypeError(f"{name} must be a C-contiguous numpy array of complex64")
+        if in_.ndim != out.ndim:
+            raise ValueError("require same ndim on input and output")
+        if in_.ndim == 2:
+            batch = in_.shape[0]
+            if in_.shape[0] != out.shape[0]:
+                raise ValueError("require equal batch size on input and output")
+            nin, nout = in_.shape[1], out.shape[1]
+        elif in_.ndim == 1:
+            batch, nin, nout = 1, in_.shape[0], out.shape[0]
+        else:
+            raise ValueError("require 1D or 2D data")
+        if nin != self._input_size:
+            raise ValueError("unexpected input length")
+        if nout != self._output_size:
+            raise ValueError("unexpected output length")
+        self._check(self._lib.i3b_rangecomp_execute(self._handle, out.ctypes.data, in_.ctypes.data, batch, 0))
+
+    def last_device_ms(self) -> float:
+        return float(self._lib.i3b_rangecomp_last_device_ms(self._handle))
+
+    def close(self):
+        if getattr(self, "_handle", None):
+            self._lib.i3b_rangecomp_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

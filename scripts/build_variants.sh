@@ -8,6 +8,6 @@ NV="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler 
 while [ $# -gt 1 ]; do
   name=$1; flags=$2; shift 2
   /usr/local/cuda/bin/nvcc $NV $flags -c accumulate_fast.cu -o build/variants/fast_$name.o
-  /usr/local/cuda/bin/nvcc -shared -o build/variants/lib_$name.so build/capi.o build/solve_kernels.o build/peaks.o build/variants/fast_$name.o -lpthread
+  /usr/local/cuda/bin/nvcc -shared -o build/variants/lib_$name.so build/capi.o build/solve_kernels.o build/peaks.o build/rangecomp.o build/variants/fast_$name.o -lpthread -lcufft
   echo built $name
 done
