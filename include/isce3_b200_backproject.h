@@ -229,7 +229,11 @@ enum {
     I3B_FLAG_FORCE_GENERIC = 1u << 0,
     /* `in` / `out` / `height` are DEVICE pointers on the current device
      * (no staging copies); single device only                              */
-    I3B_FLAG_DEVICE_POINTERS = 1u << 1
+    I3B_FLAG_DEVICE_POINTERS = 1u << 1,
+    /* only `in` is a DEVICE pointer on the current device (e.g. the output of
+     * i3b_rangecomp_execute_to_device): the swath never crosses the host link;
+     * `out` / `height` stay host arrays; single device only                 */
+    I3B_FLAG_DEVICE_INPUT = 1u << 2
 };
 
 /* Per-call measurements, filled by i3b_last_stats() for the last successful
@@ -330,6 +334,13 @@ int i3b_rangecomp_query(const I3B_RangeComp* rc, int* fft_size, int* output_size
  * following i3b_backproject with the same flag).                              */
 int i3b_rangecomp_execute(I3B_RangeComp* rc, float* out, const float* in, int batch,
                           uint32_t flags);
+/* Range-compress `lines` host lines (any number: processed in chunks of maxbatch) into ONE
+ * newly allocated device array complex64 [lines][output_size], returned in *dev_out and owned
+ * by the caller (i3b_device_free); feed it to i3b_backproject with I3B_FLAG_DEVICE_INPUT.   */
+int i3b_rangecomp_execute_to_device(I3B_RangeComp* rc, const float* in, int64_t lines,
+                                    float** dev_out);
+int i3b_device_free(void* device_pointer);
+int i3b_device_to_host(void* dst, const void* device_src, size_t bytes);
 double i3b_rangecomp_last_device_ms(const I3B_RangeComp* rc);
 const char* i3b_rangecomp_last_error(void);
 int i3b_rangecomp_destroy(I3B_RangeComp* rc);

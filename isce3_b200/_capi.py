@@ -47,6 +47,7 @@ ERROR_STRINGS = {
 }
 
 FLAG_FORCE_GENERIC = 1
+FLAG_DEVICE_INPUT = 4
 FLAG_DEVICE_POINTERS = 2
 
 KERNEL_BARTLETT, KERNEL_LINEAR, KERNEL_KNAB, KERNEL_TABULATED, KERNEL_CHEBY = range(5)
@@ -244,6 +245,9 @@ EXPORTED_SYMBOLS = (
     "i3b_rangecomp_create",
     "i3b_rangecomp_query",
     "i3b_rangecomp_execute",
+    "i3b_rangecomp_execute_to_device",
+    "i3b_device_free",
+    "i3b_device_to_host",
     "i3b_rangecomp_last_device_ms",
     "i3b_rangecomp_last_error",
     "i3b_rangecomp_destroy",
@@ -294,6 +298,12 @@ def load_library() -> C.CDLL:
     lib.i3b_rangecomp_query.restype = C.c_int
     lib.i3b_rangecomp_execute.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32]
     lib.i3b_rangecomp_execute.restype = C.c_int
+    lib.i3b_rangecomp_execute_to_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]
+    lib.i3b_rangecomp_execute_to_device.restype = C.c_int
+    lib.i3b_device_free.argtypes = [C.c_void_p]
+    lib.i3b_device_free.restype = C.c_int
+    lib.i3b_device_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.i3b_device_to_host.restype = C.c_int
     lib.i3b_rangecomp_last_device_ms.argtypes = [C.c_void_p]
     lib.i3b_rangecomp_last_device_ms.restype = C.c_double
     lib.i3b_rangecomp_last_error.restype = C.c_char_p

@@ -256,7 +256,7 @@ static void validate(const I3B_BackprojectArgs& a)
     const double width = k.kind == I3B_KERNEL_LINEAR ? 2.0 : k.width;
     if (!(width > 0) || std::ceil(width) > 1024) bad("unsupported kernel width");
     if (a.n_devices < 0 || (a.n_devices > 0 && !a.devices)) bad("bad device list");
-    if ((a.flags & I3B_FLAG_DEVICE_POINTERS) && a.n_devices > 1)
+    if ((a.flags & (I3B_FLAG_DEVICE_POINTERS | I3B_FLAG_DEVICE_INPUT)) && a.n_devices > 1)
         bad("device-pointer mode is single-device only");
 }
 
@@ -534,7 +534,7 @@ static void shard_run(const HostScene& hs, Shard& sh, bool resident_only)
     Event ea0, ea1;
     double ms_h2d = 0.0;
     if (klast > kfirst && sh.ap.npix > 0) {
-        const bool devptr = (a.flags & I3B_FLAG_DEVICE_POINTERS) != 0;
+        const bool devptr = (a.flags & (I3B_FLAG_DEVICE_POINTERS | I3B_FLAG_DEVICE_INPUT)) != 0;
         if (!sh.rc_resident) {
             if (devptr && (nr % 2 == 0)) {
                 sh.rc_dev = reinterpret_cast<const float2*>(a.in);

@@ -272,6 +272,66 @@ int i3b_rangecomp_execute(I3B_RangeComp* rc, float* out, const float* in, int ba
     });
 }
 
+int i3b_rangecomp_execute_to_device(I3B_RangeComp* rc, const float* in, int64_t lines, float** dev_out)
+{
+    return rc_guarded([&]() {
+        if (!rc || !in || !dev_out) throw RcError(I3B_EXC_INVALID_ARGUMENT, "null argument");
+        *dev_out = nullptr;
+        if (lines < 1) throw RcError(I3B_EXC_DOMAIN_ERROR, "number of lines must be > 0");
+        RC_CK(cudaSetDevice(rc->device));
+        cudaStream_t s = rc->stream;
+        const int n_in = rc->input_size, n_out = rc->out_size, nfft = rc->fft_size;
+        float2* d_all = nullptr;
+        RC_CK(cudaMalloc(&d_all, (size_t) lines * n_out * sizeof(float2)));
+        const int offset = rc->mode == I3B_RANGECOMP_FULL ? 0
+                           : rc->mode == I3B_RANGECOMP_VALID ? rc->chirp_size - 1 : rc->chirp_size / 2;
+        double ms_total = 0.0;
+        try {
+            cudaEvent_t e0, e1;
+            RC_CK(cudaEventCreate(&e0));
+            RC_CK(cudaEventCreate(&e1));
+            for (int64_t l0 = 0; l0 < lines; l0 += rc->max_batch) {
+                const int batch = (int) std::min<int64_t>(rc->max_batch, lines - l0);
+                RC_CK(cudaMemcpyAsync(rc->d_in, in + 2 * (size_t) l0 * n_in, (size_t) batch * n_in * sizeof(float2),
+                                      cudaMemcpyHostToDevice, s));
+                RC_CK(cudaEventRecord(e0, s));
+                const long long tot = (long long) batch * nfft, tout = (long long) batch * n_out;
+                rc_pad_kernel<<<grid_for(tot), 256, 0, s>>>(rc->d_work, rc->d_in, n_in, nfft, tot);
+                cufftHandle plan = rc->plan_for(batch);
+                RC_FFT(cufftExecC2C(plan, rc->d_work, rc->d_work, CUFFT_FORWARD));
+                rc_multiply_kernel<<<grid_for(tot), 256, 0, s>>>(rc->d_work, rc->d_ref, nfft, tot);
+                RC_FFT(cufftExecC2C(plan, rc->d_work, rc->d_work, CUFFT_INVERSE));
+                rc_crop_kernel<<<grid_for(tout), 256, 0, s>>>(d_all + (size_t) l0 * n_out, rc->d_work, n_out, nfft,
+                                                            offset, tout);
+                RC_CK(cudaGetLastError());
+                RC_CK(cudaEventRecord(e1, s));
+                RC_CK(cudaStreamSynchronize(s)); // d_in is reused by the next chunk
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, e0, e1);
+                ms_total += ms;
+            }
+            cudaEventDestroy(e0);
+            cudaEventDestroy(e1);
+        } catch (...) {
+            cudaFree(d_all);
+            throw;
+        }
+        rc->ms_last = ms_total;
+        *dev_out = reinterpret_cast<float*>(d_all);
+        return 0;
+    });
+}
+
+int i3b_device_free(void* p)
+{
+    return cudaFree(p) == cudaSuccess ? 0 : I3B_EXC_CUDA_ERROR;
+}
+
+int i3b_device_to_host(void* dst, const void* src, size_t bytes)
+{
+    return cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : I3B_EXC_CUDA_ERROR;
+}
+
 double i3b_rangecomp_last_device_ms(const I3B_RangeComp* rc) { return rc ? rc->ms_last : 0.0; }
 
 int i3b_rangecomp_destroy(I3B_RangeComp* rc)

@@ -66,7 +66,40 @@ def parse_geo2rdr_params(params: dict) -> _capi.Geo2RdrBracketParams:
     return out
 
 
+class DeviceLines:
+    """complex64 [lines][samples] living in HBM (output of ``RangeComp.rangecompress_to_device``);
+    pass it as ``in_`` of ``backproject`` and the swath never crosses the host link."""
+
+    dtype = np.dtype(np.complex64)
+    ndim = 2
+
+    def __init__(self, pointer: int, shape):
+        self.pointer, self.shape = int(pointer), tuple(int(x) for x in shape)
+
+    def to_host(self) -> np.ndarray:
+        out = np.empty(self.shape, np.complex64)
+        status = _capi.load_library().i3b_device_to_host(out.ctypes.data, self.pointer, out.nbytes)
+        if status < 0:
+            raise CudaError("device to host copy failed")
+        return out
+
+    def free(self):
+        if self.pointer:
+            _capi.load_library().i3b_device_free(self.pointer)
+            self.pointer = 0
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 def _check_array(a, name, dtype, shape, what):
+    if isinstance(a, DeviceLines) and name == "input":
+        if tuple(a.shape) != tuple(shape):
+            raise InvalidArgument(f"{what} shape must match {name} radar grid shape")
+        return
     if not isinstance(a, np.ndarray) or a.dtype != dtype:
         raise TypeError(f"{name} must be a numpy array of {np.dtype(dtype).name}")
     if a.ndim != 2:
@@ -107,7 +140,11 @@ def build_args(out, out_geometry, in_, in_geometry, dem, fc, ds, kernel,
     a.abi_version = _capi.ABI_VERSION
     a.flags = _capi.FLAG_FORCE_GENERIC if force_generic else 0
     a.out = out.ctypes.data if out is not None else None
-    a.in_ = in_.ctypes.data
+    if isinstance(in_, DeviceLines):
+        a.flags |= _capi.FLAG_DEVICE_INPUT
+        a.in_ = in_.pointer
+    else:
+        a.in_ = in_.ctypes.data
     a.height = height.ctypes.data if height is not None else None
     fl.keep += [out, in_, height]
     a.out_geometry = _capi.flatten_geometry(out_geometry, fl)
@@ -334,6 +371,20 @@ class RangeComp:
         if nout != self._output_size:
             raise ValueError("unexpected output length")
         self._check(self._lib.i3b_rangecomp_execute(self._handle, out.ctypes.data, in_.ctypes.data, batch, 0))
+
+    def rangecompress_to_device(self, in_) -> "DeviceLines":
+        """Range-compress all lines of ``in_`` (2-D, any number of lines: chunks of ``maxbatch``)
+        and leave the result in HBM (extension; see I3B_FLAG_DEVICE_INPUT)."""
+        if not isinstance(in_, np.ndarray) or in_.dtype != np.complex64 or not in_.flags.c_contiguous:
+            raise TypeError("in must be a C-contiguous numpy array of complex64")
+        if in_.ndim != 2:
+            raise ValueError("require 2D data")
+        if in_.shape[1] != self._input_size:
+            raise ValueError("unexpected input length")
+        ptr = C.c_void_p()
+        self._check(self._lib.i3b_rangecomp_execute_to_device(self._handle, in_.ctypes.data, in_.shape[0],
+                                                              C.byref(ptr)))
+        return DeviceLines(ptr.value, (in_.shape[0], self._output_size))
 
     def last_device_ms(self) -> float:
         return float(self._lib.i3b_rangecomp_last_device_ms(self._handle))

@@ -136,3 +136,43 @@ def test_gpu_argument_errors_mirror_the_binding():
         focus.RangeComp(np.ones(4, np.complex64), 0)
     with pytest.raises(focus.DomainError):
         focus.RangeComp(np.ones(4, np.complex64), 8, maxbatch=0)
+
+
+@gpu
+def test_gpu_range_compressed_swath_stays_in_hbm_for_backprojection(oracle):
+    """Raw -> range compression -> backprojection without the swath going back to the host:
+    point-target raw echoes (the range-compressed synthetic scene convolved with the chirp,
+    so that compressing them gives the chirp's autocorrelation around each target) are
+    compressed on the GPU into HBM and focused from there; the result equals focusing the
+    host copy of the same compressed data, and matches the CPU reference on it."""
+    from isce3_b200 import synth
+    from isce3_b200.focus import RangeComp, backproject, last_stats
+    sc = synth.make_scene("c2", pulses=2048, bins=1024, out_lines=16, out_samples=200, n_targets=1, noise_db=False)
+    chirp = orc.form_linear_chirp(20e6 / 20e-6, 20e-6, 24e6)           # 481 samples
+    chirp = (chirp / np.sqrt(np.sum(np.abs(chirp) ** 2))).astype(np.complex64)
+    # "raw" data: each RC line spread by the chirp (full convolution), so that matched
+    # filtering in mode Valid returns lines of the original length
+    raw = np.stack([np.convolve(line, chirp) for line in sc.rc]).astype(np.complex64)
+    rc = RangeComp(chirp, raw.shape[1], maxbatch=300, mode=RangeComp.Mode.Valid)
+    assert rc.output_size == sc.rc.shape[1]
+    dev = rc.rangecompress_to_device(raw)
+    host = dev.to_host()
+    want = orc.rangecompress(chirp, raw, orc.VALID)
+    assert np.linalg.norm(host - want) <= 2e-6 * np.linalg.norm(want)
+    shape = (sc.out_geometry.grid_length, sc.out_geometry.grid_width)
+    args = list(sc.backproject_args())
+    out_dev = np.zeros(shape, np.complex64)
+    args[1] = dev
+    assert backproject(out_dev, *args) is False
+    assert last_stats()["h2d_bytes"] == 0
+    out_host = np.zeros(shape, np.complex64)
+    args[1] = host
+    backproject(out_host, *args)
+    assert np.linalg.norm(out_dev - out_host) <= 1e-6 * np.linalg.norm(out_host)
+    ref = np.zeros(shape, np.complex64)
+    oracle.backproject(ref, *args)
+    assert np.linalg.norm(out_dev - ref) <= 1e-4 * np.linalg.norm(ref)
+    # and the image still shows the target where it was placed
+    tg = sc.targets[0]
+    assert np.unravel_index(np.argmax(np.abs(out_dev)), shape) == (int(tg.az_index), int(tg.rg_index))
+    dev.free()
