@@ -996,7 +996,9 @@ static FitResult fit_kernel(const DevKernel& k, double tol)
 
 constexpr double FIT_TOL = 3e-5;
 
-static bool taps_supported(int K) { return K == 8 || K == 9 || K == 16 || K == 32; }
+// instantiated tap counts: every width up to 13 (a thread keeps all K weights and the K+1
+// sample window in registers), then 16 and 32 (chunked MAC)
+static bool taps_supported(int K) { return (K >= 3 && K <= 13) || K == 16 || K == 32; }
 
 // Index of the baked table (tap_poly_imm.h) equal to this fit, or -1.  "Equal" = every
 // coefficient within 2e-7 absolute: the two fits then give weights that differ by less than
@@ -1048,7 +1050,7 @@ int fast_fit(const DevKernel& hk, I3B_TapPolyFit* fit, char* why, size_t why_len
         }
     fit->imm_variant = imm_enabled() ? match_imm_table(R) : -1;
     if (!taps_supported(hk.taps)) {
-        snprintf(why, why_len, "tap count %d has no fast instantiation (8, 9, 16, 32)", hk.taps);
+        snprintf(why, why_len, "tap count %d has no fast instantiation (3..13, 16, 32)", hk.taps);
         return 0;
     }
     if (!R.ok) {
@@ -1176,8 +1178,17 @@ int launch_accumulate_fast(const AccumParams& P, const DevKernel& hk, const Pixe
     cudaError_t e = cudaMemcpyToSymbolAsync(c_poly, R.rows, sizeof(R.rows), 0, cudaMemcpyHostToDevice, s);
     if (e != cudaSuccess) return (int) e;
     switch (K) {
+    case 3: return launch_inst<3, 6, CoefBank>(L);
+    case 4: return launch_inst<4, 7, CoefBank>(L);
+    case 5: return launch_inst<5, 6, CoefBank>(L);
+    case 6: return launch_inst<6, 7, CoefBank>(L);
+    case 7: return launch_inst<7, 6, CoefBank>(L);
     case 8: return launch_inst<8, 7, CoefBank>(L);
     case 9: return launch_inst<9, 6, CoefBank>(L);
+    case 10: return launch_inst<10, 7, CoefBank>(L);
+    case 11: return launch_inst<11, 6, CoefBank>(L);
+    case 12: return launch_inst<12, 7, CoefBank>(L);
+    case 13: return launch_inst<13, 6, CoefBank>(L);
     case 16: return launch_inst<16, 7, CoefBank>(L);
     case 32: return launch_inst<32, 7, CoefBank>(L);
     default: return -1;

@@ -118,6 +118,16 @@ def test_irf_metrics_match_oracle(oracle):
     assert dr * ig["range"]["resolution"] <= core.speed_of_light / (2 * sc.range_bandwidth)
 
 
+@pytest.mark.parametrize("taps", [3, 4, 5, 6, 7, 10, 11, 12, 13])
+def test_every_instantiated_tap_count(oracle, taps):
+    """Kernel widths other than the workflow default: each has a fast instantiation."""
+    sc = synth.make_scene("c1", pulses=640, bins=1024, out_lines=8, out_samples=136, taps=taps,
+                          noise_db=-20.0)
+    gpu = run_gpu(sc)
+    assert gpu[3]["taps"] == taps and gpu[3]["used_fast_kernel"] == 1
+    check(gpu, run_cpu(oracle, sc), sc)
+
+
 @pytest.mark.parametrize("taps", [8, 16, 32])
 def test_airborne_kernel_widths(oracle, taps):
     sc = synth.make_scene("c5", pulses=6144, bins=1536, out_lines=12, out_samples=200, n_targets=1,
@@ -300,8 +310,17 @@ def test_other_kernel_types(oracle, kernel):
          "tab5": lambda: core.TabulatedKernelF32(core.KnabKernel(5.0, 0.8), 512)}[kernel]()
     sc.kernel = k
     gpu = run_gpu(sc)
-    fast_expected = kernel in ("cheby", "knab")
-    assert gpu[3]["used_fast_kernel"] == (1 if fast_expected else 0)
+    # piecewise-linear kernels have no per-tap polynomial form; the others take the fast
+    # kernel whenever the host-side fit meets its residual bound (tab5: a coarse 512-point table)
+    from isce3_b200 import _capi
+    import ctypes
+    fl = _capi.Flattened()
+    fit = _capi.TapPolyFit()
+    _capi.load_library().i3b_fit_tap_polynomials(ctypes.byref(_capi.flatten_kernel(k, fl)), ctypes.byref(fit))
+    assert fit.supported == (0 if kernel in ("linear", "bartlett") else fit.supported)
+    assert gpu[3]["used_fast_kernel"] == fit.supported
+    if kernel in ("cheby", "knab"):
+        assert fit.supported == 1
     # Cheby/Knab<float> kernels are evaluated in float by the reference: allow their rounding
     check(gpu, run_cpu(oracle, sc), sc, rms_tol=2e-4 if kernel == "knab" else RMS_TOL)
 
