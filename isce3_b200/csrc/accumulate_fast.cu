@@ -86,7 +86,11 @@ struct __align__(16) TapPoly {
     float e[MAX_COEF / 2];
     float o[MAX_COEF / 2];
 };
-__constant__ TapPoly c_poly[MAX_TAPS / 2 + 1];
+// The fitted rows travel as a kernel parameter (constant bank 0), not in a __constant__
+// symbol: concurrent calls on one device with different kernels must not share them.
+struct PolyTable {
+    TapPoly rows[MAX_TAPS / 2 + 1];
+};
 
 // ---- PTX wrappers --------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p)
@@ -244,8 +248,8 @@ __device__ __forceinline__ double2 lds_d2(uint32_t addr)
 // CoefImm<V> only when the run-time fit of the caller's kernel equals table V.
 struct CoefBank {
     static constexpr bool kImm = false;
-    __device__ static __forceinline__ float e(int m, int i) { return c_poly[m].e[i]; }
-    __device__ static __forceinline__ float o(int m, int i) { return c_poly[m].o[i]; }
+    __device__ static __forceinline__ float e(int, int) { return 0.f; } // (rows come through Top::bank)
+    __device__ static __forceinline__ float o(int, int) { return 0.f; }
 };
 template<int V>
 struct CoefImm {
@@ -269,11 +273,13 @@ struct Weights {
     struct Top {
         float e[(K + 1) / 2];
         float o[K / 2 > 0 ? K / 2 : 1];
+        uint32_t bank; // general kernel: shared-memory address of the fitted rows
     };
     // `zero` is a kernel parameter that is always 0: adding it to the bit pattern keeps ptxas
     // from constant-propagating the value back into per-pulse immediate moves.
-    __device__ static __forceinline__ void load_top(Top& t, int zero)
+    __device__ static __forceinline__ void load_top(Top& t, int zero, uint32_t bank)
     {
+        t.bank = bank;
         if (kHoist) {
 #pragma unroll
             for (int m = 0; m < (K + 1) / 2; ++m)
@@ -300,8 +306,8 @@ struct Weights {
                 cov[NO - 1] = top.o[m];
             }
         } else {
-            const float4 ce = *reinterpret_cast<const float4*>(c_poly[m].e);
-            const float4 co = *reinterpret_cast<const float4*>(c_poly[m].o);
+            // broadcast LDS.128 (all lanes the same address): they issue in the FFMA2 shadow
+            const float4 ce = lds128(top.bank + 32u * m), co = lds128(top.bank + 32u * m + 16u);
             cev[0] = ce.x; cev[1] = ce.y; cev[2] = ce.z; cev[3] = ce.w;
             cov[0] = co.x; cov[1] = co.y; cov[2] = co.z; cov[3] = co.w;
         }
@@ -335,8 +341,7 @@ struct Weights {
                     cov[NO - 1] = top.o[m];
                 }
             } else {
-                const float4 ce = *reinterpret_cast<const float4*>(c_poly[m].e);
-                const float4 co = *reinterpret_cast<const float4*>(c_poly[m].o);
+                const float4 ce = lds128(top.bank + 32u * m), co = lds128(top.bank + 32u * m + 16u);
                 cev[0] = ce.x; cev[1] = ce.y; cev[2] = ce.z; cev[3] = ce.w;
                 cov[0] = co.x; cov[1] = co.y; cov[2] = co.z; cov[3] = co.w;
             }
@@ -357,7 +362,7 @@ struct Weights {
                 for (int i = 0; i < 4; ++i) cev[i] = Coef::e(m, i);
                 if (kHoist) cev[NE - 1] = top.e[m];
             } else {
-                const float4 ce = *reinterpret_cast<const float4*>(c_poly[m].e);
+                const float4 ce = lds128(top.bank + 32u * m);
                 cev[0] = ce.x; cev[1] = ce.y; cev[2] = ce.z; cev[3] = ce.w;
             }
             f32x2 e = bcast2(cev[NE - 1]);
@@ -543,11 +548,11 @@ template<int K, int D, class Coef, bool EDGE>
 __device__ __forceinline__ void tile_body(PairState& S, float& jf, unsigned& jjmax,
                                           uint32_t lines_addr, uint32_t row_bytes, int wlo,
                                           unsigned jmax, float Gr, unsigned krel0, unsigned krel1,
-                                          int zero)
+                                          int zero, uint32_t bank)
 {
     typedef Weights<K, D, Coef> WT;
     typename WT::Top top;
-    WT::load_top(top, zero);
+    WT::load_top(top, zero, bank);
     const int iw0 = S.i0rel[0] - wlo, iw1 = S.i0rel[1] - wlo;
     uint32_t line_addr = lines_addr;
     // (wide kernels: the body is already hundreds of instructions per pulse)
@@ -637,14 +642,15 @@ __device__ __forceinline__
 #endif
 void tile_body_edge(PairState& S, float& jf, unsigned& jjmax, uint32_t lines_addr,
                     uint32_t row_bytes, int wlo, unsigned jmax, float Gr, unsigned krel0,
-                    unsigned krel1, int zero)
+                    unsigned krel1, int zero, uint32_t bank)
 {
-    tile_body<K, D, Coef, true>(S, jf, jjmax, lines_addr, row_bytes, wlo, jmax, Gr, krel0, krel1, zero);
+    tile_body<K, D, Coef, true>(S, jf, jjmax, lines_addr, row_bytes, wlo, jmax, Gr, krel0, krel1, zero, bank);
 }
 
 template<int K, int D, class Coef>
 __global__ void __launch_bounds__(NTHREADS, 2)
-accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, FastParams P,
+accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, const __grid_constant__ PolyTable poly,
+                       FastParams P,
                        const PixelRec* __restrict__ pix, const PulseRec* __restrict__ pulse,
                        double2* __restrict__ acc, const TileInfo* __restrict__ tiles,
                        DevStatus* status)
@@ -681,6 +687,15 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, FastParams P,
     constexpr int LOWOFF = (K & 1) ? -(K / 2) : 1 - K / 2;
     constexpr double SHIFT = (K & 1) ? 0.5 : 0.0;
 
+    // general kernel: the fitted polynomial rows, from the kernel parameter to shared memory
+    const uint32_t poly_addr = smem_u32(smem_raw + POLY_OFFSET);
+    if (!Coef::kImm) {
+        constexpr int NF = (int) (sizeof(PolyTable) / sizeof(float));
+        static_assert(POLY_OFFSET + sizeof(PolyTable) <= HEADER_BYTES, "polynomial rows overflow the header");
+        const float* src = reinterpret_cast<const float*>(&poly);
+        float* dst = reinterpret_cast<float*>(smem_raw + POLY_OFFSET);
+        for (int i = tid; i < NF; i += NTHREADS) dst[i] = src[i];
+    }
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; ++s) {
             mbar_init(&hdr->full[s], 1);
@@ -868,9 +883,9 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, FastParams P,
         const unsigned krel0 = (unsigned) (kt - S.kstart[0]);
         const unsigned krel1 = (unsigned) (kt - S.kstart[1]);
         if (I3B_EDGE_SPLIT && kt >= ks_max && kt + TK <= ke_min)
-            tile_body<K, D, Coef, false>(S, jf, jjmax, lines_addr, row_bytes, wlo, jmax, Gr, krel0, krel1, P.zero);
+            tile_body<K, D, Coef, false>(S, jf, jjmax, lines_addr, row_bytes, wlo, jmax, Gr, krel0, krel1, P.zero, poly_addr);
         else
-            tile_body_edge<K, D, Coef>(S, jf, jjmax, lines_addr, row_bytes, wlo, jmax, Gr, krel0, krel1, P.zero);
+            tile_body_edge<K, D, Coef>(S, jf, jjmax, lines_addr, row_bytes, wlo, jmax, Gr, krel0, krel1, P.zero, poly_addr);
 
         // pulse tile done: fold FP32 partials into FP64, release the stage.
         // sum s*e^{j phi} = (P.x - Q.y) + j (P.y + Q.x)
@@ -1087,6 +1102,7 @@ static EncodeTiledFn get_encode_fn()
 
 struct LaunchArgs {
     const CUtensorMap* map;
+    const PolyTable* poly;
     const FastParams* FP;
     const PixelRec* pix;
     const PulseRec* pulse;
@@ -1104,7 +1120,7 @@ static int launch_inst(const LaunchArgs& L)
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) L.smem);
     if (e != cudaSuccess) return (int) e;
     const unsigned grid = (unsigned) (L.FP->tiles_rg * L.FP->tiles_az);
-    kern<<<grid, NTHREADS, L.smem, L.s>>>(*L.map, *L.FP, L.pix, L.pulse, L.acc, L.tiles, L.status);
+    kern<<<grid, NTHREADS, L.smem, L.s>>>(*L.map, *L.poly, *L.FP, L.pix, L.pulse, L.acc, L.tiles, L.status);
     return (int) cudaGetLastError();
 }
 
@@ -1168,15 +1184,15 @@ int launch_accumulate_fast(const AccumParams& P, const DevKernel& hk, const Pixe
     FP.fc = P.fc;
     FP.zero = 0;
     const size_t smem = HEADER_BYTES + NSTAGE * stage_bytes(W) + (size_t) NTHREADS * 6 * PX * sizeof(double);
-    const LaunchArgs L{&map, &FP, pix, pulse, acc, tiles, status, smem, s};
+    PolyTable PT;
+    std::memcpy(PT.rows, R.rows, sizeof PT.rows);
+    const LaunchArgs L{&map, &PT, &FP, pix, pulse, acc, tiles, status, smem, s};
 
     const int v = imm_enabled() ? match_imm_table(R) : -1;
     if (v >= 0) {
         const int r = launch_imm<0>(v, L);
         if (r >= 0) return r;
     }
-    cudaError_t e = cudaMemcpyToSymbolAsync(c_poly, R.rows, sizeof(R.rows), 0, cudaMemcpyHostToDevice, s);
-    if (e != cudaSuccess) return (int) e;
     switch (K) {
     case 3: return launch_inst<3, 6, CoefBank>(L);
     case 4: return launch_inst<4, 7, CoefBank>(L);
