@@ -158,10 +158,12 @@ def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return 0
+    cores = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(cores)  # torchrun exports 1; the reference uses every core
     from oracle import tdbp
+    tdbp.set_threads(cores)
     oracle = tdbp.best()
     sc = make_scene(args)
-    cores = os.cpu_count() or 1
     og = sc.out_geometry
     # bounded sample: a few azimuth lines x full range width, sized for ~10 s per step
     pulses_per_pixel = min(sc.in_geometry.grid_length, 4400)
@@ -368,8 +370,9 @@ def run_ours(args):
     cpu = None
     if not args.no_cpu:
         from oracle import tdbp
-        oracle = tdbp.best()
         cores = os.cpu_count() or 1
+        tdbp.set_threads(cores)  # torchrun exports OMP_NUM_THREADS=1 to its workers
+        oracle = tdbp.best()
         ppx = pp_rank / max(shape[0] * shape[1], 1)
         lines = max(1, int(2.5e8 * cores / 8 / max(ppx * og.grid_width, 1)))
         dt, b0, n, ref = cpu_sample(sc, oracle, lines)

@@ -269,4 +269,12 @@ def best() -> Oracle:
 
 
 def set_threads(n: int):
+    """Thread count of the OpenMP oracles.  torchrun exports OMP_NUM_THREADS=1 to its workers,
+    which would make the "all host cores" CPU baseline single-threaded: set the environment
+    for a runtime that is not initialised yet, and tell an initialised one directly."""
     os.environ["OMP_NUM_THREADS"] = str(n)
+    try:
+        gomp = C.CDLL("libgomp.so.1")
+        gomp.omp_set_num_threads(int(n))
+    except OSError:
+        pass
