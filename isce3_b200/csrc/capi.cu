@@ -577,7 +577,12 @@ static void shard_run(const HostScene& hs, Shard& sh, bool resident_only)
                 sh.stats.h2d_bytes += (int64_t) rows * nr * (int64_t) sizeof(float2);
                 if (resident_only) continue;
                 const bool first = k == kfirst, last = k + rows >= klast;
-                if (first || last || cudaStreamQuery(s) == cudaSuccess) {
+                // I3B_LAUNCH_PER_SLAB=1 (test knob): one launch per slab, like the reference
+                static const bool per_slab = [] {
+                    const char* e = std::getenv("I3B_LAUNCH_PER_SLAB");
+                    return e && std::atoi(e) != 0;
+                }();
+                if (first || last || per_slab || cudaStreamQuery(s) == cudaSuccess) {
                     CK(cudaStreamWaitEvent(s, landed.back()->e, 0));
                     shard_accumulate(sh, pending, k + rows, s);
                     pending = k + rows;

@@ -116,20 +116,12 @@ target_solve_kernel(SolveParams P, PixelRec* __restrict__ pix, float* __restrict
             const int jl = (int) (tid / P.out_width), i = (int) (tid % P.out_width);
             tile = (jl / P.tile_az) * P.tiles_rg + i / P.tile_rg;
         }
+        // lanes that share a tile reduce among themselves (hardware warp reduce over the peer
+        // mask: correct for any grouping, e.g. warps that straddle two lines or two tiles)
         const unsigned peers = __match_any_sync(0xffffffffu, tile);
-        int tmin = kmin, tmax = kmax, tbad = (tid < npix && kstart < 0) ? 1 : 0;
-        // reduce over the peer group (lanes of one tile are contiguous in a warp, but stay general)
-        for (int o = 16; o > 0; o >>= 1) {
-            const int src = (threadIdx.x & 31) ^ o;
-            const int omin = __shfl_xor_sync(0xffffffffu, tmin, o);
-            const int omax = __shfl_xor_sync(0xffffffffu, tmax, o);
-            const int obad = __shfl_xor_sync(0xffffffffu, tbad, o);
-            if (peers & (1u << src)) {
-                tmin = min(tmin, omin);
-                tmax = max(tmax, omax);
-                tbad |= obad;
-            }
-        }
+        const int tmin = __reduce_min_sync(peers, kmin);
+        const int tmax = __reduce_max_sync(peers, kmax);
+        const int tbad = (int) __reduce_or_sync(peers, (tid < npix && kstart < 0) ? 1u : 0u);
         const int leader = __ffs(peers) - 1;
         if (tile >= 0 && (int) (threadIdx.x & 31) == leader) {
             if (tmin != INT_MAX) atomicMin(&tiles[tile].kmin, tmin);

@@ -280,6 +280,40 @@ def test_fused_output_encoding_matches_the_workflow_writer():
         backproject(out, *sc.backproject_args(), mantissa_nbits=24)
 
 
+def test_one_launch_per_slab_equals_one_launch(oracle):
+    """Many accumulation launches over narrow pulse slabs (I3B_LAUNCH_PER_SLAB=1 is read at
+    first use, so this runs in a fresh process): every pixel still integrates exactly its
+    own aperture -- per-tile pulse spans, aperture-edge tiles and cross-launch FP64 sums --
+    for an output width that is not a multiple of the warp or tile size."""
+    import subprocess
+    import sys
+    code = """
+import numpy as np, sys
+from isce3_b200 import synth
+from isce3_b200.focus import backproject, last_stats
+sc = synth.make_scene("c2", pulses=3072, bins=1024, out_lines=37, out_samples=203, n_targets=1)
+shape = (37, 203)
+a = np.zeros(shape, np.complex64); b = np.zeros(shape, np.complex64)
+backproject(a, *sc.backproject_args(), batch=53)
+na = last_stats()["accumulate_launches"]
+backproject(b, *sc.backproject_args(), batch=100000)
+nb = last_stats()["accumulate_launches"]
+rel = float(np.linalg.norm(a - b) / np.linalg.norm(b))
+# one pulse missing (or counted twice) in one pixel would change it by ~ rms/sqrt(#pulses) = 2e-2 rms;
+# different FP32 segment alignment between the two runs changes pixels by ~1e-6 rms
+worst = float(np.max(np.abs(a - b)) / np.sqrt(np.mean(np.abs(b) ** 2)))
+print("RESULT", na, nb, rel, worst)
+assert na > 20 and nb == 1, (na, nb)
+assert rel <= 5e-6, rel
+assert worst <= 1e-4, worst
+"""
+    import os
+    env = dict(os.environ, I3B_LAUNCH_PER_SLAB="1")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env,
+                       cwd=str(__import__("pathlib").Path(__file__).resolve().parent.parent))
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
 def test_failed_pixels_are_nan_and_flagged(oracle):
     """geo2rdr bracket that excludes part of the image: those pixels are (NaN, NaN), the call
     returns True (FailedToConverge); rdr2geo failure also NaNs the height layer."""
