@@ -4,6 +4,7 @@
 // length, boundsError (Backproject.cpp:134; geometry/detail/Geo2Rdr.icc:193-221)
 // -- backed by the restated sampler in oracle/tdbp_samplers.h.
 #pragma once
+#include <isce3/core/Constants.h>
 #include <isce3/core/forward.h>
 #include <vector>
 #include "../../../tdbp_samplers.h"
@@ -33,6 +34,16 @@ public:
     double ySpacing() const { return _d.dy; }
     size_t length() const { return size_t(_d.length); }
     size_t width() const { return size_t(_d.width); }
+    // accessors the isce3-side adapter (integration/.../BackprojectB200.cpp) reads
+    isce3::core::dataInterpMethod interpMethod() const
+    {
+        return static_cast<isce3::core::dataInterpMethod>(_d.method);
+    }
+    struct DataView { // stands for Matrix<T>: only .data() is used
+        const T* p;
+        const T* data() const { return p; }
+    };
+    DataView data() const { return DataView {reinterpret_cast<const T*>(_d.data)}; }
     bool contains(double y, double x) const { return tdbp_oracle::lut2d_contains(_d, y, x); }
     T eval(double y, double x) const { return T(tdbp_oracle::lut2d_eval(_d, y, x)); }
 private:

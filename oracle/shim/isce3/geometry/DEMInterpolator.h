@@ -7,6 +7,7 @@
 #pragma once
 #include <memory>
 #include <isce3/core/Projections.h>
+#include <isce3/core/Constants.h>
 #include <isce3/core/forward.h>
 #include <isce3/geometry/forward.h>
 #include "../../../tdbp_samplers.h"
@@ -20,6 +21,18 @@ public:
     int epsgCode() const { return _d.epsg; }
     double refHeight() const { return _d.ref_height; }
     bool haveRaster() const { return _d.have_raster != 0; }
+    // accessors the isce3-side adapter reads (geometry/DEMInterpolator.h:96-188)
+    isce3::core::dataInterpMethod interpMethod() const
+    {
+        return static_cast<isce3::core::dataInterpMethod>(_d.method);
+    }
+    double xStart() const { return _d.xstart; }
+    double yStart() const { return _d.ystart; }
+    double deltaX() const { return _d.dx; }
+    double deltaY() const { return _d.dy; }
+    size_t width() const { return size_t(_d.width); }
+    size_t length() const { return size_t(_d.length); }
+    const float* data() const { return _d.data; }
     double interpolateLonLat(double lon, double lat) const
     {
         // DEMInterpolator.cpp:592-611

@@ -26,6 +26,7 @@ HERE = Path(__file__).resolve().parent
 PORT_LIB = HERE / "libtdbp_oracle.so"
 REF_LIB = HERE / "_ref" / "libtdbp_ref.so"
 REFCUDA_LIB = HERE / "_ref" / "libtdbp_refcuda.so"
+ADAPTER_LIB = HERE / "_ref" / "libtdbp_adapter.so"
 
 BRENT_FN = C.CFUNCTYPE(C.c_double, C.c_double, C.c_void_p)
 
@@ -249,6 +250,40 @@ class ReferenceCuda:
             raise RuntimeError(f"reference CUDA status {status}: "
                                f"{(self.lib.tdbp_refcuda_last_error() or b'').decode()}")
         return status != 0
+
+
+class Isce3Adapter:
+    """integration/isce3/cuda/focus/BackprojectB200.cpp compiled against the reference's
+    headers: builds the reference's own objects from the flat arguments and calls
+    isce3::cuda::focus::backproject, i.e. the adapter, which calls the product library."""
+
+    def __init__(self, path: Path = ADAPTER_LIB):
+        self.lib = C.CDLL(str(path))
+        self._backproject = self.lib.tdbp_adapter_backproject
+        self._backproject.restype = C.c_int
+        self._backproject.argtypes = [C.POINTER(_capi.BackprojectArgs)]
+        self.lib.tdbp_adapter_last_error.restype = C.c_char_p
+
+    def backproject(self, out, out_geometry, in_, in_geometry, dem, fc, ds, kernel,
+                    dry_tropo_model="tsx", rdr2geo_params=None, geo2rdr_params=None, batch=1024,
+                    height=None):
+        fl = build_args(out, out_geometry, in_, in_geometry, dem, fc, ds, kernel,
+                        dry_tropo_model, rdr2geo_params, geo2rdr_params, batch, height)
+        status = self._backproject(C.byref(fl.args))
+        if status < 0:
+            raise RuntimeError(f"adapter status {status}: "
+                               f"{(self.lib.tdbp_adapter_last_error() or b'').decode()}")
+        return status != 0
+
+
+def have_adapter() -> bool:
+    return ADAPTER_LIB.exists()
+
+
+def adapter() -> Isce3Adapter:
+    if "adapter" not in _cache:
+        _cache["adapter"] = Isce3Adapter()
+    return _cache["adapter"]
 
 
 def have_ref_cuda() -> bool:
