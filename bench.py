@@ -433,6 +433,9 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "reference_cuda": ref_cuda,
         "target_solve_ms_per_step": solve_ms / args.steps,
+        # CUDA-event time of the two kernels that make up a resident step (rank 0); the
+        # difference to ms_per_step (wall, barrier to barrier) is finalisation + host overhead
+        "device_ms_per_step": kernel_ms_step + solve_ms / args.steps,
     }
     print(json.dumps(line), flush=True)
     if dist is not None:
