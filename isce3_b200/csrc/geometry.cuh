@@ -523,8 +523,22 @@ __device__ inline int geo2rdr_bracket(D3 x, const DevOrbit& orbit, const DevLUT2
     };
     int err = I3B_INVALID_INTERVAL;
     if (t_guess == t_guess) {
-        const double lo = fmax(t_guess - 4.0, t0), hi = fmin(t_guess + 4.0, t1);
-        if (lo < hi) err = brent(lo, hi, doppler_error, prm.tol_aztime, aztime);
+        // When input and output geometry share orbit and Doppler model the guess IS the root
+        // (geo2rdr inverts rdr2geo): a sign change across [guess - tol/2, guess + tol/2] proves
+        // the root lies within tol/2 of the guess -- the accuracy the root finder itself
+        // stops at -- for two evaluations instead of a search.
+        const double hw = 0.5 * prm.tol_aztime;
+        if (hw > 0.0 && t_guess - hw >= t0 && t_guess + hw <= t1) {
+            const double fa = doppler_error(t_guess - hw), fb = doppler_error(t_guess + hw);
+            if (fa == fa && fb == fb && opposite_sign(fa, fb)) {
+                *aztime = t_guess;
+                err = I3B_SUCCESS;
+            }
+        }
+        if (err != I3B_SUCCESS) {
+            const double lo = fmax(t_guess - 4.0, t0), hi = fmin(t_guess + 4.0, t1);
+            if (lo < hi) err = brent(lo, hi, doppler_error, prm.tol_aztime, aztime);
+        }
     }
     if (err != I3B_SUCCESS) err = brent(t0, t1, doppler_error, prm.tol_aztime, aztime);
     if (err != I3B_SUCCESS) return err;
