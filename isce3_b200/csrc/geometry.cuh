@@ -475,7 +475,28 @@ __device__ inline int rdr2geo_bracket(double aztime, double slant_range, double 
         const double cguess = (re * re - dot(center, center) - radius * radius) /
                               (2.0 * radius * dot(radar, down));
         if (fabs(cguess) < 1.0) {
-            const double g = acos(cguess);
+            double g = acos(cguess);
+            // Newton on the height error from that guess: d(height)/d(look) is the ellipsoid
+            // normal at the point dotted with the tangent of the range/Doppler circle.  Accepted
+            // only when the residual height proves the look angle is within tol_look / 2 of the
+            // root (|dh| <= |dh/dlook| * tol_look / 2), i.e. the root finder's own accuracy.
+#pragma unroll 1
+            for (int it = 0; it < 4; ++it) {
+                double sl, cl;
+                sincos(g, &sl, &cl);
+                const D3 X = center + (radius * sl) * horizontal + (radius * cl) * down;
+                const double e = xyz_to_height(X) - dem.ref_height;
+                const D3 n = unit(D3 {X.x, X.y, X.z / (1.0 - kE2)});
+                const double slope = dot(n, (radius * cl) * horizontal - (radius * sl) * down);
+                if (!(fabs(slope) > 1e-3 * radius)) break; // grazing geometry: leave it to Brent
+                if (fabs(e) <= 0.5 * tol_look * fabs(slope) && g >= prm.look_min && g <= prm.look_max) {
+                    *xyz = X;
+                    return I3B_SUCCESS;
+                }
+                g -= e / slope;
+                if (!(g == g)) break;
+            }
+            g = acos(cguess);
             const double lo = fmax(g - 0.02, prm.look_min), hi = fmin(g + 0.02, prm.look_max);
             if (lo < hi && brent(lo, hi, dh_flat, tol_look, &look) == I3B_SUCCESS) {
                 *xyz = get_xyz(look);
