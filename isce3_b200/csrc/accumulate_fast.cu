@@ -2,25 +2,31 @@
 // hot loop, sumCoherent of cxx/isce3/focus/Backproject.cpp:30-63, re-designed for B200.
 //
 //  * CTA = 8 warps.  A CTA owns a tile of TILE_AZ x TILE_RG output pixels; every thread
-//    owns PX = 2 range-adjacent pixels; warp 0 doubles as the TMA producer.
-//  * The producer streams pulse tiles (TK range-compressed lines clipped to the
-//    range window the CTA's pixels can touch, plus the TK per-pulse orbit records) into
-//    a multi-stage shared-memory ring with TMA (cp.async.bulk.tensor.2d + cp.async.bulk)
-//    completing on mbarriers; out-of-swath samples arrive as zeros (TMA OOB fill), which
-//    IS the CPU reference's zero-padded edge window (core/detail/Interp1d.h:54-80).
-//  * Slant range stays FP64 (|x-p|^2 by FMA, sqrt by one Newton step from a linear
-//    predictor), phase and sample index are split into integer/fraction with
-//    magic-number adds, so no FP64<->FP32/int conversion instruction is issued in the loop.
+//    owns PX = 2 range-adjacent pixels; the TMA producer role rotates over the warps.
+//    Tiles are numbered azimuth-major inside groups of GROUP_RG range columns so that
+//    co-resident CTAs share pulse lines in L2.
+//  * The producer streams pulse tiles (TK range-compressed lines clipped to the range
+//    window the CTA's pixels can touch) into a multi-stage shared-memory ring with TMA
+//    (cp.async.bulk.tensor.2d) completing on mbarriers; out-of-swath samples arrive as
+//    zeros (TMA OOB fill), which IS the CPU reference's zero-padded edge window
+//    (core/detail/Interp1d.h:54-80).
+//  * Geometry in FP64 only at 64-pulse segment boundaries (exact carrier phase from an
+//    80-byte per-pulse record); inside a segment the phase is a cubic in FP32 and the
+//    sample coordinate an affine function of it, both pixels of a thread packed in FFMA2.
+//    Integer / fraction of the coordinate are split with a magic-number add: no FP64 and
+//    no conversion instruction per pulse.
 //  * Interpolation weights: per-tap polynomials in the fractional sample offset, fitted on
-//    the host to the caller's kernel (table-lerp, Chebyshev or Knab) and read from the
-//    constant bank as FFMA operands -- no shared-memory weight gathers.  Taps m and
-//    K-1-m share even/odd parts (the kernels are even functions).
+//    the host to the caller's kernel (table-lerp, Chebyshev or Knab).  Kernels with a
+//    build-time coefficient table (tap_poly_imm.h) take the coefficients as FFMA2
+//    immediates; any other kernel reads them from shared memory (broadcast LDS.128).
+//    Taps m and K-1-m share even/odd parts (the kernels are even functions).
 //  * The two pixels of a thread share one register window of K+1 samples read with
-//    LDS.128 (stride-16B across lanes: conflict-free).
+//    LDS.128 (stride-16B across lanes: conflict-free); 16- and 32-tap kernels process the
+//    window in chunks of 4 tap pairs.
 //
 // Numerics vs the reference: weights differ from table-lerp by the fit residual (checked
-// on the host, <= 3e-5 abs), phase fraction is quantised to 2^-23 cycle, partial sums are
-// FP32 within a pulse tile and FP64 across tiles.
+// on the host, <= 3e-5 abs), the FP32 phase carries ~1e-5 rad by the end of a segment,
+// partial sums are FP32 within a pulse tile and FP64 across tiles and launches.
 #include <cuda.h>
 
 #include <algorithm>
@@ -48,10 +54,10 @@ constexpr int TILE_RG = 128;  // output range pixels per CTA tile
 #endif
 constexpr int TILE_AZ = I3B_TILE_AZ;   // output azimuth lines per CTA tile
 constexpr int PX = 2;         // pixels per thread (range-adjacent)
-constexpr int NTHREADS = TILE_AZ * TILE_RG / PX; // 256 threads; warp 0 is also the producer
+constexpr int NTHREADS = TILE_AZ * TILE_RG / PX; // 256 threads
 constexpr int TK = 16;        // pulses per stage
 constexpr int NSTAGE = I3B_NSTAGE;
-constexpr int POLY_OFFSET = 256;   // per-tap polynomial rows (copied from constant memory)
+constexpr int POLY_OFFSET = 256;   // per-tap polynomial rows (copied from the kernel parameter)
 #ifndef I3B_ROTATE_PRODUCER
 #define I3B_ROTATE_PRODUCER 1
 #endif
@@ -72,9 +78,6 @@ constexpr int GROUP_RG = I3B_GROUP_RG; // range columns per azimuth-major tile g
 static_assert(PREFETCH >= 1 && PREFETCH < I3B_NSTAGE, "prefetch distance must be in [1, NSTAGE)");
 constexpr int NWARPS_ROT = TILE_AZ * TILE_RG / 2 / 32;
 constexpr int HEADER_BYTES = 1024; // barriers, window origins, corner pixels, polynomial rows
-#ifndef I3B_POLY_SMEM
-#define I3B_POLY_SMEM 0
-#endif
 constexpr int MAX_TAPS = 32;
 constexpr int MAX_COEF = 8;   // degree <= 7
 
@@ -161,7 +164,6 @@ struct FastParams {
     int zero;       // always 0 (opaque to the compiler, see Weights::load_top)
 };
 
-constexpr double MAGIC = 805306368.0; // 1.5 * 2^29: ulp 2^-23, integer part in mantissa bits 23..
 
 // Shared-memory carve-up (dynamic): per stage [TK][W] float2 then [TK] PulseRec.
 struct SmemHeader {
