@@ -810,16 +810,17 @@ int i3b_backproject(const I3B_BackprojectArgs* args)
         float* out = args->out;
         float* height = args->height;
         double t_setup = 0, t_solve = 0, t_run = 0, t_down = 0;
+        const bool single = plan->shards.size() == 1; // phase laps: single-shard calls only
         for_each_shard(*plan, [&](Shard& sh) {
             shard_setup(plan->hs, sh);
-            t_setup = lap();
+            if (single) t_setup = lap();
             // the one-shot call streams from the caller's buffer (no deep copy of `in`)
             shard_solve(plan->hs, sh);
-            t_solve = lap();
+            if (single) t_solve = lap();
             shard_run(plan->hs, sh, false);
-            t_run = lap();
+            if (single) t_run = lap();
             shard_download(plan->hs, sh, out, height);
-            t_down = lap();
+            if (single) t_down = lap();
         });
         I3B_Plan* raw = plan.get();
         const int status = merge_status(*raw);
@@ -827,7 +828,7 @@ int i3b_backproject(const I3B_BackprojectArgs* args)
         merge_stats(*raw, ms_work);
         plan.reset(); // device memory is released inside the timed call
         g_last_stats.ms_total = lap();
-        if (std::getenv("I3B_DEBUG_TIMING"))
+        if (single && std::getenv("I3B_DEBUG_TIMING"))
             fprintf(stderr, "[i3b] setup %.1f solve %.1f run %.1f download %.1f teardown %.1f total %.1f ms\n",
                     t_setup, t_solve - t_setup, t_run - t_solve, t_down - t_run,
                     g_last_stats.ms_total - ms_work, g_last_stats.ms_total);
