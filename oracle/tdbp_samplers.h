@@ -224,30 +224,36 @@ inline double dem_interp_xy(const I3B_DEM& d, double x, double y)
 // own createProj()->forward() (Projections.cpp compiled unchanged).
 namespace proj {
 
-// Projections.cpp:36-46
-inline double clens(const double* a, int size, double real)
+// Clenshaw summation of sum_k a[k] sin((k+1) B)  (what Projections.cpp:36-46 computes)
+inline double clens(const double* a, int size, double B)
 {
-    const double* p;
-    double hr, hr1, hr2;
-    for (p = a + size, hr2 = 0., hr1 = *(--p), hr = 0.; a - p; hr2 = hr1, hr1 = hr)
-        hr = -hr2 + (2. * hr1 * std::cos(real)) + *(--p);
-    return std::sin(real) * hr;
+    const double two_cos = 2.0 * std::cos(B);
+    double u_next = 0.0, u = a[size - 1];
+    for (int k = size - 2; k >= 0; --k) {
+        const double t = two_cos * u - u_next + a[k];
+        u_next = u;
+        u = t;
+    }
+    return std::sin(B) * u;
 }
 
-// Projections.cpp:58-82
-inline double clenS(const double* a, int size, double real, double imag, double& R, double& I)
+// Complex-argument Clenshaw summation (Projections.cpp:58-82): real and imaginary part of
+// sum_k a[k] sin((k+1)(B + i C))
+inline double clenS(const double* a, int size, double B, double C, double& R, double& I)
 {
-    const double* p;
-    double hr, hr1, hr2, hi, hi1, hi2;
-    for (p = a + size, hr2 = 0., hi2 = 0., hi1 = 0., hr1 = *(--p), hr = 0., hi = 0.; a - p;
-         hr2 = hr1, hi2 = hi1, hr1 = hr, hi1 = hi) {
-        hr = -hr2 + (2. * hr1 * std::cos(real) * std::cosh(imag)) -
-             (-2. * hi1 * std::sin(real) * std::sinh(imag)) + *(--p);
-        hi = -hi2 + (-2. * hr1 * std::sin(real) * std::sinh(imag)) +
-             (2. * hi1 * std::cos(real) * std::cosh(imag));
+    const double sB = std::sin(B), cB = std::cos(B), shC = std::sinh(C), chC = std::cosh(C);
+    const double pr = 2.0 * cB * chC, pi = -2.0 * sB * shC; // 2 cos(B + iC)
+    double ur = a[size - 1], ui = 0.0, ur_next = 0.0, ui_next = 0.0;
+    for (int k = size - 2; k >= 0; --k) {
+        const double tr = pr * ur - pi * ui - ur_next + a[k];
+        const double ti = pi * ur + pr * ui - ui_next;
+        ur_next = ur;
+        ui_next = ui;
+        ur = tr;
+        ui = ti;
     }
-    R = (std::sin(real) * std::cosh(imag) * hr) - (std::cos(real) * std::sinh(imag) * hi);
-    I = (std::sin(real) * std::cosh(imag) * hi) + (std::cos(real) * std::sinh(imag) * hr);
+    R = sB * chC * ur - cB * shC * ui;
+    I = sB * chC * ui + cB * shC * ur;
     return R;
 }
 
