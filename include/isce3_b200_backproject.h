@@ -309,6 +309,10 @@ int i3b_last_stats(I3B_Stats* stats);
 const char* i3b_last_error(void);
 const char* i3b_version(void);
 int i3b_device_count(void);
+/* The calling thread's current CUDA device (-1: none).  Every entry point of this library
+ * leaves it as it found it (the reference never changes it either: the caller selects the
+ * device once, focus.py:1592-1593).                                          */
+int i3b_current_device(void);
 int i3b_measure_peaks(int device, I3B_Peaks* peaks);
 /* Return device memory cached by earlier calls to the driver (all devices). */
 int i3b_release_device_memory(void);

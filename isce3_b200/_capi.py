@@ -239,6 +239,7 @@ EXPORTED_SYMBOLS = (
     "i3b_last_error",
     "i3b_version",
     "i3b_device_count",
+    "i3b_current_device",
     "i3b_measure_peaks",
     "i3b_fit_tap_polynomials",
     "i3b_release_device_memory",

@@ -398,6 +398,7 @@ struct PairState {
     int i0rel[PX];     // window start at the base minus the magic bias (window origin added per tile)
     f32x2 accp[PX], accq[PX]; // FP32 partial sums of the pulse tile: sum cos*(re,im), sum sin*(re,im)
     int kstart[PX], kspan[PX]; // aperture: kstart <= k < kstart + kspan
+    float flim;        // steady sub-tiles: 1/2 - bound on what the cubic's curvature adds between checks
 };
 
 #ifndef I3B_SEG
@@ -546,7 +547,7 @@ struct ChunkedMac {
 // FADD2 / FMUL2 2.1 cycles, scalar FFMA / IMAD / FMUL 2.0 (no cheaper than the packed form),
 // FADD 1.4, LOP3 / IADD3 / VIMNMX 0.6-0.9, MOV / LDS ~0.2 (issue in the FFMA2 shadow), MUFU 8
 // XU cycles (asynchronous).  So the loop is written to be FFMA2-only on the FMA pipe.
-template<int K, int D, class Coef, bool EDGE>
+template<int K, int D, class Coef, bool EDGE, int NP>
 __device__ __forceinline__ void tile_body(PairState& S, float& jf, unsigned& jjmax,
                                           uint32_t lines_addr, uint32_t row_bytes, int wlo,
                                           unsigned jmax, float Gr, unsigned krel0, unsigned krel1,
@@ -560,7 +561,7 @@ __device__ __forceinline__ void tile_body(PairState& S, float& jf, unsigned& jjm
     // (wide kernels: the body is already hundreds of instructions per pulse)
     constexpr int kUnroll = (K >= 16) ? 1 : KK_UNROLL;
 #pragma unroll kUnroll
-    for (int kk = 0; kk < TK; ++kk) {
+    for (int kk = 0; kk < NP; ++kk) {
         // keep the staged line address a loop-carried register (ptxas otherwise rebuilds it
         // from the shared-memory base every pulse: ~10 instructions)
         asm volatile("" : "+r"(line_addr));
@@ -646,7 +647,73 @@ void tile_body_edge(PairState& S, float& jf, unsigned& jjmax, uint32_t lines_add
                     uint32_t row_bytes, int wlo, unsigned jmax, float Gr, unsigned krel0,
                     unsigned krel1, int zero, uint32_t bank)
 {
-    tile_body<K, D, Coef, true>(S, jf, jjmax, lines_addr, row_bytes, wlo, jmax, Gr, krel0, krel1, zero, bank);
+    tile_body<K, D, Coef, true, TK>(S, jf, jjmax, lines_addr, row_bytes, wlo, jmax, Gr, krel0, krel1, zero, bank);
+}
+
+
+// ---- steady sub-tiles --------------------------------------------------------------------
+// Over a handful of pulses the sample coordinate of a pixel moves by a small fraction of a
+// sample (range migration is <= ~1e-2 samples per pulse), so for most runs of I3B_SUB pulses
+// the INTEGER part of the coordinate -- the window position -- is the same for every pulse
+// of the run and the two pixels of a thread keep adjacent windows.  Such a run ("steady
+// sub-tile", proven before it starts from the phase cubic itself: values at both ends plus
+// a curvature bound) needs no per-pulse rounding, index arithmetic, clamping or branching:
+// the window address advances by one staged row per pulse, the parity of the window start
+// is a compile-time constant of the loop, and the fraction is ONE FFMA2 from the phase.
+// The loop is straight-line code (fully unrolled, pulse offsets are immediates), which also
+// lets ptxas overlap the phase / sincos / loads of the next pulses with the FMA work of the
+// current one.  Runs that are not steady take tile_body (per-pulse rounding), bit-for-bit
+// the same arithmetic as before.
+#ifndef I3B_STEADY
+#define I3B_STEADY 1
+#endif
+#ifndef I3B_SUB
+#define I3B_SUB 8
+#endif
+constexpr int SUB = I3B_SUB; // pulses per steady run
+static_assert(TK % SUB == 0, "a staged pulse tile is a whole number of steady runs");
+
+template<int K, int D, class Coef, int OFF, int NP>
+__device__ __forceinline__ void subtile_steady(PairState& S, f32x2 A0, f32x2 A1, f32x2 A2, f32x2 A3,
+                                               f32x2 fbase, float Gr, uint32_t src, uint32_t row_bytes,
+                                               int zero, uint32_t bank)
+{
+    typedef Weights<K, D, Coef> WT;
+    typename WT::Top top;
+    WT::load_top(top, zero, bank);
+#pragma unroll
+    for (int x = 0; x < NP; ++x) {
+        // carrier phase of both pixels x pulses into the run (cubic re-centred on the run)
+        f32x2 ang = A0;
+        if (x > 0) {
+            const f32x2 X = bcast2((float) x);
+            ang = fma2(fma2(fma2(A3, X, A2), X, A1), X, A0);
+        }
+        const f32x2 f = fma2(ang, bcast2(Gr), fbase); // centred fraction (integer part is fixed)
+        float ang0, ang1, cs0, sn0, cs1, sn1;
+        unpack2(ang, ang0, ang1);
+        sincos_fast(ang0, sn0, cs0);
+        sincos_fast(ang1, sn1, cs1);
+        if constexpr (K >= 16 && K % 8 == 0) {
+            const f32x2 h = mul2(f, f), nf = mul2(f, bcast2(-1.0f));
+            f32x2 lo[6], hi[6], a0 = 0ull, a1 = 0ull;
+            ChunkedMac<K, D, Coef, OFF>::run(f, h, nf, src, lo, hi, a0, a1, top);
+            rotate_accumulate<false>(S, a0, a1, cs0, sn0, cs1, sn1, true, true);
+        } else {
+            constexpr int NV = (K + 3) / 2;
+            f32x2 sm[2 * NV];
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const float4 v4 = lds128(src + 16u * i);
+                sm[2 * i] = pack2(v4.x, v4.y);
+                sm[2 * i + 1] = pack2(v4.z, v4.w);
+            }
+            f32x2 w[K];
+            WT::eval(f, w, top);
+            mac_rotate<K, OFF, false>(S, w, sm, cs0, sn0, cs1, sn1, true, true);
+        }
+        src += row_bytes;
+    }
 }
 
 template<int K, int D, class Coef>
@@ -776,13 +843,20 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, const __grid_
     const int ks_max = hdr->ks_max, ke_min = hdr->ke_min;
     if (hdr->bad) return; // (tile table says the same)
     if (kb >= ke) return; // nothing to integrate in this launch
-    const int ntiles = (ke - kb + TK - 1) / TK;
+    // Pulse tiles and geometry segments sit on ABSOLUTE pulse indices (multiples of TK / SEG),
+    // not on the first pulse this CTA happens to integrate in this launch: every FP32 tile
+    // sum, every phase cubic and the order of the FP64 additions are then properties of the
+    // pixel alone, so the image does not depend on how the pulses were cut into launches
+    // (`batch`, upload timing) nor on how the grid was cut into shards.  The host keeps
+    // launch boundaries on multiples of TK (fast_pulse_tile()).
+    const int t0 = (kb / TK) * TK; // kb >= 0
+    const int ntiles = (ke - t0 + TK - 1) / TK;
 
     // Producer role (one warp, all lanes converge here): stage pulse tile n.
     auto produce = [&](int n) {
         const int s = n % NSTAGE;
         if (n >= NSTAGE) mbar_wait(&hdr->empty[s], ((n / NSTAGE) - 1) & 1);
-        const int kfirst = kb + n * TK;
+        const int kfirst = t0 + n * TK;
         const int klast = kfirst + TK - 1; // the pulse table is padded past the last pulse
         // range window from the 4 corner pixels at the first/last pulse of the tile
         double u = 0.;
@@ -804,6 +878,7 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, const __grid_
             hdr->winlo[s] = wlo;
             unsigned char* sp = stage0 + (size_t) s * sbytes;
             mbar_arrive_expect_tx(&hdr->full[s], (uint32_t) ((size_t) TK * P.W * sizeof(float2)));
+            // rows before / after the staged swath (kfirst < rc_k0, ...) arrive as zeros
             tma_load_2d(sp, &rc_map, wlo, kfirst - P.rc_k0, &hdr->full[s]);
         }
         __syncwarp();
@@ -817,16 +892,26 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, const __grid_
     double* slot = reinterpret_cast<double*>(smem_raw + HEADER_BYTES + NSTAGE * sbytes) + tid * (6 * PX);
     double* accd = slot;          // [2 * PX]
     double* ybnd = slot + 2 * PX; // [PX][4]  T(b - SEG), T(b), T(b + SEG), T(b + 2 SEG)
-#pragma unroll
-    for (int i = 0; i < 2 * PX; ++i) accd[i] = 0.0;
-    // boundaries b_i = kb + SEG * i; evaluate T at b_{-1}, b_0, b_1 (b_2 comes with segment 0)
+    // The FP64 sums CONTINUE from what earlier launches left in `acc`: one sequential chain
+    // of additions per pixel whatever the launch partition (bit-reproducible image).
 #pragma unroll
     for (int p = 0; p < PX; ++p) {
-        const PixelRec q = pix[gidx[p]];
-        const double xx = q.x * q.x + q.y * q.y + q.z * q.z, t0 = P.fc * q.tau_atm;
-        ybnd[4 * p + 1] = exact_cycles(q, xx, t0, pulse[kb - SEG]);
-        ybnd[4 * p + 2] = exact_cycles(q, xx, t0, pulse[kb]);
-        ybnd[4 * p + 3] = exact_cycles(q, xx, t0, pulse[kb + SEG]);
+        const double2 a = acc[gidx[p]];
+        accd[2 * p] = a.x;
+        accd[2 * p + 1] = a.y;
+    }
+    // segment boundaries are multiples of SEG; evaluate T at the three around the first segment
+    // (the fourth comes with the segment)
+    {
+        const int b0 = t0 & ~(SEG - 1);
+#pragma unroll
+        for (int p = 0; p < PX; ++p) {
+            const PixelRec q = pix[gidx[p]];
+            const double xx = q.x * q.x + q.y * q.y + q.z * q.z, tc = P.fc * q.tau_atm;
+            ybnd[4 * p + 1] = exact_cycles(q, xx, tc, pulse[b0 - SEG]);
+            ybnd[4 * p + 2] = exact_cycles(q, xx, tc, pulse[b0]);
+            ybnd[4 * p + 3] = exact_cycles(q, xx, tc, pulse[b0 + SEG]);
+        }
     }
 
     unsigned jjmax = 0; // sticky maximum of the (unsigned) window offsets: overflow detector
@@ -836,22 +921,25 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, const __grid_
     const double TWO_PI_D = 6.283185307179586476925;
     const float Gr = (float) (P.G / TWO_PI_D); // samples per radian of carrier phase
     float jf = 0.f;                             // pulse index within the segment
+    int seg_b = 0;                              // first pulse of the current segment
 
     for (int n = 0; n < ntiles; ++n) {
         if (n + PREFETCH < ntiles && warp == (I3B_ROTATE_PRODUCER ? (n + PREFETCH) % NWARPS_ROT : 0))
             produce(n + PREFETCH);
 
-        if ((n % (SEG / TK)) == 0) {
+        const int kt = t0 + n * TK; // first pulse of the tile
+        if (n == 0 || (kt & (SEG - 1)) == 0) {
             // ---- new geometry segment: one exact FP64 evaluation per pixel, cubic through
             // the four surrounding boundaries, everything inside the segment is FP32 ----
-            const int b = kb + n * TK;
+            const int b = kt & ~(SEG - 1);
+            seg_b = b;
             float c1[PX], c2[PX], c3[PX], a0[PX], f0[PX];
 #pragma unroll
             for (int p = 0; p < PX; ++p) {
                 const PixelRec q = pix[gidx[p]];
-                const double xx = q.x * q.x + q.y * q.y + q.z * q.z, t0 = P.fc * q.tau_atm;
+                const double xx = q.x * q.x + q.y * q.y + q.z * q.z, tc = P.fc * q.tau_atm;
                 const double y0 = ybnd[4 * p + 1], y1 = ybnd[4 * p + 2], y2 = ybnd[4 * p + 3];
-                const double y3 = exact_cycles(q, xx, t0, pulse[b + 2 * SEG]);
+                const double y3 = exact_cycles(q, xx, tc, pulse[b + 2 * SEG]);
                 ybnd[4 * p + 1] = y1;
                 ybnd[4 * p + 2] = y2;
                 ybnd[4 * p + 3] = y3;
@@ -873,21 +961,74 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, const __grid_
             S.ang0 = pack2(a0[0], a0[1]);
             // the loop evaluates coordinate = f0m + Gr * (ang0 + increment)
             S.f0m = pack2(f0[0] - Gr * a0[0], f0[1] - Gr * a0[1]);
-            jf = 0.f;
+            // what the cubic's curvature can add to the coordinate between the two ends of a
+            // steady run: |u''| (SUB-1)^2 / 8, u'' = Gr (2 c2 + 6 c3 j), j < SEG
+            const float curv0 = 2.f * fabsf(c2[0]) + (6.f * SEG) * fabsf(c3[0]);
+            const float curv1 = 2.f * fabsf(c2[1]) + (6.f * SEG) * fabsf(c3[1]);
+            S.flim = 0.5f - 1e-5f - fabsf(Gr) * fmaxf(curv0, curv1) * ((SUB - 1) * (SUB - 1) / 8.0f);
         }
 
         const int s = n % NSTAGE;
         mbar_wait(&hdr->full[s], (n / NSTAGE) & 1);
         const uint32_t lines_addr = stage_addr0 + (uint32_t) s * (uint32_t) sbytes;
         const int wlo = hdr->winlo[s];
-        const int kt = kb + n * TK;
-        // k - kstart for the first pulse of the tile, per pixel
-        const unsigned krel0 = (unsigned) (kt - S.kstart[0]);
-        const unsigned krel1 = (unsigned) (kt - S.kstart[1]);
-        if (I3B_EDGE_SPLIT && kt >= ks_max && kt + TK <= ke_min)
-            tile_body<K, D, Coef, false>(S, jf, jjmax, lines_addr, row_bytes, wlo, jmax, Gr, krel0, krel1, P.zero, poly_addr);
-        else
-            tile_body_edge<K, D, Coef>(S, jf, jjmax, lines_addr, row_bytes, wlo, jmax, Gr, krel0, krel1, P.zero, poly_addr);
+        if (I3B_EDGE_SPLIT && kt >= ks_max && kt + TK <= ke_min) {
+#if I3B_STEADY
+            const int iw0 = S.i0rel[0] - wlo, iw1 = S.i0rel[1] - wlo;
+#pragma unroll 1
+            for (int sub = 0; sub < TK / SUB; ++sub) {
+                const float js = (float) (kt - seg_b + sub * SUB);
+                const uint32_t la = lines_addr + (uint32_t) (sub * SUB) * row_bytes;
+                // phase cubic re-centred on the run: ang(js + x) = A0 + A1 x + A2 x^2 + A3 x^3
+                const f32x2 js2 = bcast2(js), Gr2 = bcast2(Gr);
+                const f32x2 c3x3 = mul2(S.c3, bcast2(3.0f)), c2x2 = add2(S.c2, S.c2);
+                const f32x2 A2 = fma2(c3x3, js2, S.c2);
+                const f32x2 A1 = fma2(fma2(c3x3, js2, c2x2), js2, S.c1);
+                const f32x2 A0 = fma2(fma2(fma2(S.c3, js2, S.c2), js2, S.c1), js2, S.ang0);
+                const f32x2 XE = bcast2((float) (SUB - 1));
+                const f32x2 ange = fma2(fma2(fma2(S.c3, XE, A2), XE, A1), XE, A0);
+                // coordinate (minus floor(base) + 1/2) at both ends of the run
+                const f32x2 g0 = fma2(A0, Gr2, S.f0m), ge = fma2(ange, Gr2, S.f0m);
+                const f32x2 mm = add2(g0, bcast2(MAGIC32));
+                const f32x2 tt = add2(mm, bcast2(-MAGIC32)); // integer part at the first pulse
+                const f32x2 fa = sub2(g0, tt), fe = sub2(ge, tt);
+                float m0, m1, fa0, fa1, fe0, fe1;
+                unpack2(mm, m0, m1);
+                unpack2(fa, fa0, fa1);
+                unpack2(fe, fe0, fe1);
+                const unsigned jj0 = (unsigned) (iw0 + __float_as_int(m0));
+                const unsigned jj1 = (unsigned) (iw1 + __float_as_int(m1));
+                const float worst = fmaxf(fmaxf(fabsf(fa0), fabsf(fa1)), fmaxf(fabsf(fe0), fabsf(fe1)));
+                // steady: same integer part over the whole run (both pixels), adjacent windows
+                // inside the staged rows
+                if (worst <= S.flim && jj1 == jj0 + 1u && jj0 < jmax) {
+                    const uint32_t src = la + ((jj0 >> 1) << 4);
+                    const f32x2 fbase = sub2(S.f0m, tt);
+                    if (jj0 & 1u)
+                        subtile_steady<K, D, Coef, 1, SUB>(S, A0, A1, A2, S.c3, fbase, Gr, src, row_bytes, P.zero, poly_addr);
+                    else
+                        subtile_steady<K, D, Coef, 0, SUB>(S, A0, A1, A2, S.c3, fbase, Gr, src, row_bytes, P.zero, poly_addr);
+                } else {
+                    jf = js;
+                    tile_body<K, D, Coef, false, SUB>(S, jf, jjmax, la, row_bytes, wlo, jmax, Gr, 0u, 0u, P.zero, poly_addr);
+                }
+            }
+#else
+            jf = (float) (kt - seg_b);
+            tile_body<K, D, Coef, false, TK>(S, jf, jjmax, lines_addr, row_bytes, wlo, jmax, Gr, 0u, 0u, P.zero, poly_addr);
+#endif
+        } else {
+            // k - kstart for the first pulse of the tile, per pixel
+            const unsigned krel0 = (unsigned) (kt - S.kstart[0]);
+            const unsigned krel1 = (unsigned) (kt - S.kstart[1]);
+            jf = (float) (kt - seg_b);
+            // (through a copy: the out-of-line call wants its argument in memory, and the
+            // interior paths should not find their pair state there)
+            PairState T = S;
+            tile_body_edge<K, D, Coef>(T, jf, jjmax, lines_addr, row_bytes, wlo, jmax, Gr, krel0, krel1, P.zero, poly_addr);
+            S.accp[0] = T.accp[0]; S.accp[1] = T.accp[1];
+            S.accq[0] = T.accq[0]; S.accq[1] = T.accq[1];
+        }
 
         // pulse tile done: fold FP32 partials into FP64, release the stage.
         // sum s*e^{j phi} = (P.x - Q.y) + j (P.y + Q.x)
@@ -906,12 +1047,7 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, const __grid_
 #pragma unroll
     for (int p = 0; p < PX; ++p) {
         const int jj = line0 + lrow, ii = col0 + lcol + p;
-        if (jj < P.out_lines && ii < P.out_width) {
-            double2 a = acc[gidx[p]];
-            a.x += accd[2 * p];
-            a.y += accd[2 * p + 1];
-            acc[gidx[p]] = a;
-        }
+        if (jj < P.out_lines && ii < P.out_width) acc[gidx[p]] = make_double2(accd[2 * p], accd[2 * p + 1]);
     }
     if (jjmax > jmax) status->window_overflow = 1;
 }
@@ -1217,6 +1353,8 @@ int fast_tiles(int out_lines, int out_width)
 {
     return ((out_width + TILE_RG - 1) / TILE_RG) * ((out_lines + TILE_AZ - 1) / TILE_AZ);
 }
+
+int fast_pulse_tile() { return TK; }
 
 void fast_tile_shape(int* tile_az, int* tile_rg)
 {

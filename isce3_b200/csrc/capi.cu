@@ -334,9 +334,12 @@ struct Shard {
     {
         // Buffers go back to the cache right after this body, on this thread: make sure
         // nothing is still running on them (error paths may leave work in flight).
+        int cur = -1;
+        if (cudaGetDevice(&cur) != cudaSuccess) cur = -1;
         if (compute || copy) cudaSetDevice(device);
         if (compute) cudaStreamSynchronize(compute);
         if (copy) cudaStreamSynchronize(copy);
+        if (cur >= 0) cudaSetDevice(cur);
     }
 };
 
@@ -347,7 +350,7 @@ using namespace i3b;
 struct I3B_Plan {
     HostScene hs;
     std::vector<std::unique_ptr<Shard>> shards;
-    bool solved = false;
+    bool executed = false; // i3b_plan_execute has produced an image to download
 };
 
 namespace i3b {
@@ -555,7 +558,7 @@ static void shard_run(const HostScene& hs, Shard& sh, bool resident_only)
         }
         ea0.record(s);
         if (sh.rc_resident) {
-            shard_accumulate(sh, kfirst, klast, s);
+            if (!resident_only) shard_accumulate(sh, kfirst, klast, s);
         } else {
             const float2* in = reinterpret_cast<const float2*>(a.in);
             const int slab = std::max(a.batch, 1);
@@ -583,9 +586,15 @@ static void shard_run(const HostScene& hs, Shard& sh, bool resident_only)
                     return e && std::atoi(e) != 0;
                 }();
                 if (first || last || per_slab || cudaStreamQuery(s) == cudaSuccess) {
+                    // launches end on absolute multiples of the staged pulse tile (the last one
+                    // at klast): the image is then bit-identical for every batch size and
+                    // whatever the host link's timing made of the launch boundaries
+                    const int tk = fast_pulse_tile();
+                    const int kend = last ? klast : ((k + rows) / tk) * tk;
+                    if (kend <= pending) continue;
                     CK(cudaStreamWaitEvent(s, landed.back()->e, 0));
-                    shard_accumulate(sh, pending, k + rows, s);
-                    pending = k + rows;
+                    shard_accumulate(sh, pending, kend, s);
+                    pending = kend;
                 }
             }
             CK(cudaStreamSynchronize(sh.copy));
@@ -695,11 +704,20 @@ static std::unique_ptr<I3B_Plan> make_plan(const I3B_BackprojectArgs* args)
     hs.a.devices = hs.devices.data();
     hs.a.n_devices = (int) hs.devices.size();
     // contiguous azimuth blocks, one per device
+    // Blocks are whole rows of fast-kernel tiles (except the last), so a pixel shares its CTA
+    // with the same neighbours however many devices there are: which staged tiles count as
+    // aperture edges -- and with it the arithmetic path of every pixel -- does not depend on
+    // the device list.
     const int lines = (int) args->out_geometry.grid.length;
-    const int nsh = (int) std::min<size_t>(hs.devices.size(), (size_t) std::max(lines, 1));
-    int line = 0;
+    int tile_az = 1, tile_rg = 1;
+    fast_tile_shape(&tile_az, &tile_rg);
+    const int units = (lines + tile_az - 1) / tile_az;
+    const int nsh = (int) std::min<size_t>(hs.devices.size(), (size_t) std::max(units, 1));
+    int line = 0, unit = 0;
     for (int i = 0; i < nsh; ++i) {
-        const int n = lines / nsh + (i < lines % nsh ? 1 : 0);
+        const int nu = units / nsh + (i < units % nsh ? 1 : 0);
+        unit += nu;
+        const int n = std::min(unit * tile_az, lines) - line;
         std::unique_ptr<Shard> sh(new Shard());
         sh->device = hs.devices[i];
         sh->line0 = line;
@@ -777,9 +795,28 @@ static void merge_stats(I3B_Plan& plan, double ms_total)
     g_last_stats = t;
 }
 
+// The library selects devices on the calling thread (shards, plan destruction, the buffer
+// cache); the caller's current device is put back on every way out of an entry point -- the
+// reference never touches it (focus.py:1592-1593 sets it once for all isce3.cuda modules).
+struct DeviceGuard {
+    int prev = -1;
+    DeviceGuard()
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) {
+            prev = -1;
+            cudaGetLastError();
+        }
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
 template<class F>
 static int guarded(F&& f)
 {
+    DeviceGuard device_guard;
     try {
         return f();
     } catch (const ApiError& e) {
@@ -870,6 +907,7 @@ int i3b_plan_execute(I3B_Plan* plan)
         });
         const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         merge_stats(*plan, ms);
+        plan->executed = true;
         return merge_status(*plan);
     });
 }
@@ -878,6 +916,8 @@ int i3b_plan_download(I3B_Plan* plan, float* out, float* height)
 {
     return guarded([&]() {
         if (!plan) throw ApiError(I3B_EXC_INVALID_ARGUMENT, "null plan");
+        if (!plan->executed)
+            throw ApiError(I3B_EXC_RUNTIME_ERROR, "i3b_plan_download before any i3b_plan_execute: no image yet");
         for_each_shard(*plan, [&](Shard& sh) { shard_download(plan->hs, sh, out, height); });
         return 0;
     });
@@ -901,6 +941,13 @@ int i3b_last_stats(I3B_Stats* stats)
 const char* i3b_last_error(void) { return g_last_error.c_str(); }
 
 const char* i3b_version(void) { return "isce3_b200 0.1.0 (sm_100a)"; }
+
+int i3b_current_device(void)
+{
+    int d = -1;
+    if (cudaGetDevice(&d) != cudaSuccess) return -1;
+    return d;
+}
 
 int i3b_device_count(void)
 {

@@ -200,15 +200,27 @@ __device__ inline D3 n_vector(double lon, double lat)
 
 // ---- 2-D samplers -----------------------------------------------------------
 
-template<typename U>
+// CLAMP: indices are clamped to the array (edge replication).  Used for LUT2d, whose
+// coordinates are only clamped to [0, n-1] (LUT2d.cpp:151-152) while the bicubic / spline
+// stencils reach up to 3 samples beyond that -- the reference reads outside its matrix
+// there (host UB); on a device that is garbage or a fault.  DEM sampling keeps the
+// reference's own [2, n-1) margin test and needs no clamp.
+template<typename U, bool CLAMP = false>
 struct Grid2d {
     const U* __restrict__ data;
     int rows, cols;
-    __device__ U operator()(int r, int c) const { return data[(size_t) r * cols + c]; }
+    __device__ U operator()(int r, int c) const
+    {
+        if (CLAMP) {
+            r = min(max(r, 0), rows - 1);
+            c = min(max(c, 0), cols - 1);
+        }
+        return data[(size_t) r * cols + c];
+    }
 };
 
-template<typename U>
-__device__ inline U bilinear(double x, double y, const Grid2d<U>& z)
+template<typename U, class G>
+__device__ inline U bilinear(double x, double y, const G& z)
 {
     const int x1 = (int) floor(x), x2 = (int) ceil(x);
     const int y1 = (int) floor(y), y2 = (int) ceil(y);
@@ -229,8 +241,8 @@ __device__ inline U catmull_rom(U p0, U p1, U p2, U p3, double tf)
             p1 * U(tf * tf * (tf * 3. - 5.) + 2.)) / U(2.);
 }
 
-template<typename U>
-__device__ inline U bicubic(double x, double y, const Grid2d<U>& z)
+template<typename U, class G>
+__device__ inline U bicubic(double x, double y, const G& z)
 {
     const int x0 = (int) floor(x), y0 = (int) floor(y);
     U rowv[4];
@@ -288,8 +300,8 @@ __device__ inline U spline_eval(double x, const U* Y, const U* R)
     return yjm + (xx * (t0 + t1));
 }
 
-template<typename U>
-__device__ inline U biquintic(double x, double y, const Grid2d<U>& z)
+template<typename U, class G>
+__device__ inline U biquintic(double x, double y, const G& z)
 {
     constexpr int N = 6;
     int i0 = (int) y, j0 = (int) x;
@@ -311,14 +323,14 @@ __device__ inline U biquintic(double x, double y, const Grid2d<U>& z)
     return spline_eval<U, N>(y - i0, HC, R);
 }
 
-template<typename U>
-__device__ inline U interp2d(int method, double x, double y, const Grid2d<U>& z)
+template<typename U, class G>
+__device__ inline U interp2d(int method, double x, double y, const G& z)
 {
     switch (method) {
-    case I3B_INTERP_BICUBIC: return bicubic<U>(x, y, z);
-    case I3B_INTERP_BIQUINTIC: return biquintic<U>(x, y, z);
+    case I3B_INTERP_BICUBIC: return bicubic<U, G>(x, y, z);
+    case I3B_INTERP_BIQUINTIC: return biquintic<U, G>(x, y, z);
     case I3B_INTERP_NEAREST: return z((int) round(y), (int) round(x));
-    default: return bilinear<U>(x, y, z);
+    default: return bilinear<U, G>(x, y, z);
     }
 }
 
@@ -329,8 +341,16 @@ __device__ inline double lut2d_eval(const DevLUT2d& l, double y, double x)
     double yi = (y - l.ystart) / l.dy;
     xi = fmin(fmax(xi, 0.0), l.width - 1.0);
     yi = fmin(fmax(yi, 0.0), l.length - 1.0);
-    const Grid2d<double> g {l.data, l.length, l.width};
-    return interp2d<double>(l.method, xi, yi, g);
+    const Grid2d<double, true> g {l.data, l.length, l.width};
+    return interp2d<double, Grid2d<double, true>>(l.method, xi, yi, g);
+}
+
+// LUT2d::contains (core/LUT2d.h:84-95)
+__device__ inline bool lut2d_contains(const DevLUT2d& l, double y, double x)
+{
+    if (!l.have_data) return true;
+    const double i = (x - l.xstart) / l.dx, j = (y - l.ystart) / l.dy;
+    return (i >= 0.0 && i <= l.width - 1.0) && (j >= 0.0 && j <= l.length - 1.0);
 }
 
 // DEMInterpolator::interpolateLonLat -> interpolateXY (DEMInterpolator.cpp:592-659): project
@@ -360,7 +380,7 @@ __device__ inline double dem_interp_lonlat(const DevDEM& d, double lon, double l
     if (irow < 2 || irow >= d.length - 1) return d.ref_height;
     if (icol < 2 || icol >= d.width - 1) return d.ref_height;
     const Grid2d<float> g {d.data, d.length, d.width};
-    return interp2d<float>(d.method, col, row, g);
+    return interp2d<float, Grid2d<float>>(d.method, col, row, g);
 }
 
 // ---- Brent's bracketing root finder ---------------------------------------------

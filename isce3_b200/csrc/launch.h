@@ -65,6 +65,10 @@ int launch_accumulate_fast(const AccumParams& P, const DevKernel& host_kernel,
 int fast_fit(const DevKernel& host_kernel, I3B_TapPolyFit* fit, char* why, size_t why_len);
 int fast_tiles(int out_lines, int out_width);
 void fast_tile_shape(int* tile_az, int* tile_rg);
+// Pulses per staged tile.  Tiles sit on absolute multiples of this; an accumulation launch
+// that is not the last one of a call must END on such a multiple, so that every FP32 tile sum
+// holds the same pulses whatever the launch partition (bit-reproducible output).
+int fast_pulse_tile();
 // The pulse table holds records for pulses [-kPulsePadLo, n_pulses + kPulsePadHi): the entries
 // outside the input grid are orbit EXTRAPOLATIONS (smooth continuation), used by the fast
 // kernel's segment-boundary evaluations and by staged tiles that run over the ends.

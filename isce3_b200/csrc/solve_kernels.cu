@@ -69,6 +69,13 @@ target_solve_kernel(SolveParams P, PixelRec* __restrict__ pix, float* __restrict
         const double t = P.out_time[j];
         const double r = P.out_range[i];
         const double fD = lut2d_eval(P.out_doppler, t, r);
+        // LUT2d with bounds_error (LUT2d.cpp:143-150): the CPU reference raises through its
+        // error channel, the reference CUDA path silently returns ref_value
+        // (gpuLUT2d.cu:178-181).  Here the lookup is clamped like bounds_error=False and the
+        // call reports the soft code OutOfBoundsLookup (checked at the solutions, not at the
+        // probes of the root finders).
+        if (P.out_doppler.bounds_error && !lut2d_contains(P.out_doppler, t, r))
+            status->soft_error = I3B_OUT_OF_BOUNDS_LOOKUP;
         PixelRec rec;
         rec.x = rec.y = rec.z = nan("");
         rec.tau_atm = 0.0;
@@ -87,6 +94,8 @@ target_solve_kernel(SolveParams P, PixelRec* __restrict__ pix, float* __restrict
             if (st != I3B_SUCCESS) {
                 status->soft_error = I3B_FAILED_TO_CONVERGE;
             } else {
+                if (P.in_doppler.bounds_error && !lut2d_contains(P.in_doppler, tc, rc))
+                    status->soft_error = I3B_OUT_OF_BOUNDS_LOOKUP;
                 D3 p, v;
                 orbit_interpolate(P.in_orbit, tc, BORDER_FILLNAN, &p, &v);
                 const double l = P.wvl * rc * (norm(p) / norm(x)) / (2. * P.ds);
