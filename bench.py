@@ -2,7 +2,7 @@
 """Bench harness for the B200 TDBP backend (contract: see README / DESIGN.md).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--config c2] [--scale S]
+                    [--config c2] [--scale S] [--no-extras]
 
 One "step" = one time-domain backprojection of the synthetic frame named by ``--config``
 (default: BASELINE.json configs[1], the NISAR L-band 20 MHz frame 16384 pulses x 12288 bins
@@ -11,12 +11,21 @@ One "step" = one time-domain backprojection of the synthetic frame named by ``--
   value   pixel.pulses/s, whole job, range-compressed swath already resident in HBM
           (i3b_plan_execute: target solve + accumulation + finalisation on device)
   e2e     same metric through the reference-facing call ``backproject(out, ...)`` with HOST
-          buffers: H2D of the swath and D2H of the image inside the timed region
+          buffers: H2D of the swath and D2H of the image inside the timed region (pinned
+          host memory; ``e2e_pageable`` repeats it from ordinary pageable numpy arrays, which is
+          what the workflow hands over, focus.py:1857-1859)
   roofline      FP32 roofline of the accumulation kernel: algorithmic flops (34 + 10 K per
                 pixel.pulse) / CUDA-event kernel time, against the FFMA rate
-                measured on this device by i3b_measure_peaks
+                measured on this device by i3b_measure_peaks; ``roofline_general`` is the same
+                frame through the general (non-baked coefficient) kernel
   cpu_baseline  the CPU oracle (oracle/_ref = reference sources compiled here when present,
-                else the restated port) on a bounded sub-block of the same frame
+                else the restated port) on a bounded sub-block of the same frame, all host
+                cores and one thread
+  configs       every other BASELINE.json shape (c1, c4, c5 with 8/16/32 taps) at this N: a few
+                steps each -- value, e2e, roofline fraction, parity against the CPU oracle
+  inlib_multi_gpu  (N > 1) rank 0 alone calls backproject(out, ..., devices=[0..N-1]) on the
+                whole frame from ONE pageable input into ONE pageable output: the in-library
+                multi-GPU driver, next to the torchrun number
 
 N > 1 (torchrun, one process per GPU): the SAME frame is cut into N contiguous azimuth
 blocks; rank r focuses block r from its own copy of the swath, no inter-GPU exchange;
@@ -25,6 +34,7 @@ time = max over ranks, value = total pixel.pulses / time ("scaling": "strong").
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -40,6 +50,10 @@ sys.path.insert(0, str(ROOT))
 
 METRIC = "pixel_pulses_per_s"
 UNIT = "pixel*pulses/s"
+NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1965e6 / 1e12
+
+BASE_SHAPES = {"c1": (2048, 4096, 512, 512), "c2": (16384, 12288, 8192, 8192),
+               "c4": (16384, 32768, 2048, 8192), "c5": (65536, 8192, 2048, 2048)}
 
 
 def algorithmic_flops_per_pp(taps: int) -> float:
@@ -110,18 +124,17 @@ def dist_env():
     return rank, world, local
 
 
-def make_scene(args):
-    from isce3_b200 import synth
-    kw = {}
-    if args.scale != 1.0:
-        base = {"c1": (2048, 4096, 512, 512), "c2": (16384, 12288, 8192, 8192),
-                "c4": (16384, 32768, 2048, 8192), "c5": (65536, 8192, 2048, 2048)}[args.config[:2]]
-        s = args.scale
-        kw = dict(pulses=max(int(base[0] * min(1.0, s * 2)), 512), bins=max(int(base[1] * s), 512),
+def make_scene(config, scale=1.0, taps=0, **extra):
+    from testkit import synth
+    kw = dict(extra)
+    if scale != 1.0:
+        base = BASE_SHAPES[config[:2]]
+        s = scale
+        kw.update(pulses=max(int(base[0] * min(1.0, s * 2)), 512), bins=max(int(base[1] * s), 512),
                   out_lines=max(int(base[2] * s), 64), out_samples=max(int(base[3] * s), 128))
-    if args.taps:
-        kw["taps"] = args.taps
-    return synth.make_scene(args.config, **kw)
+    if taps:
+        kw["taps"] = taps
+    return synth.make_scene(config, **kw)
 
 
 def block_bounds(lines, world, rank):
@@ -130,22 +143,23 @@ def block_bounds(lines, world, rank):
     return a0, a0 + q + (1 if rank < r else 0)
 
 
-def workload_name(args, sc):
+def workload_name(config, sc):
     ig, og = sc.in_geometry, sc.out_geometry
-    return (f"{args.config}: {ig.grid_length} pulses x {ig.grid_width} bins -> "
+    return (f"{config}: {ig.grid_length} pulses x {ig.grid_width} bins -> "
             f"{og.grid_length} x {og.grid_width}, {'raster' if sc.dem.have_raster else 'flat'} DEM, "
             f"{sc.dry_tropo_model}, {sc.kernel.table.size if hasattr(sc.kernel, 'table') else 0}-entry "
             f"tabulated Knab, {int(np.ceil(sc.kernel.width))} taps")
 
 
-def cpu_sample(sc, oracle, lines_wanted, seconds_target=None):
+def cpu_sample(sc, oracle, lines_wanted, cols=None):
     """Oracle on a contiguous block of azimuth lines around the frame centre."""
     og = sc.out_geometry
     L = og.grid_length
     n = max(1, min(lines_wanted, L))
     a0 = max(0, L // 2 - n // 2)
-    sub = sc.out_subgrid(a0, a0 + n)
-    out = np.zeros((n, og.grid_width), np.complex64)
+    sub = sc.out_subgrid(a0, a0 + n) if cols is None else sc.out_subgrid(a0, a0 + n, 0, cols)
+    width = og.grid_width if cols is None else cols
+    out = np.zeros((n, width), np.complex64)
     t = time.perf_counter()
     oracle.backproject(out, sub, sc.rc, sc.in_geometry, sc.dem, sc.fc, sc.ds, sc.kernel,
                        sc.dry_tropo_model, sc.rdr2geo_params, sc.geo2rdr_params)
@@ -163,7 +177,7 @@ def run_reference(args):
     from oracle import tdbp
     tdbp.set_threads(cores)
     oracle = tdbp.best()
-    sc = make_scene(args)
+    sc = make_scene(args.config, args.scale, args.taps)
     og = sc.out_geometry
     # bounded sample: a few azimuth lines x full range width, sized for ~10 s per step
     pulses_per_pixel = min(sc.in_geometry.grid_length, 4400)
@@ -184,7 +198,11 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup_ref, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": workload_name(args, sc), "sample": sample},
+        "config": {"workload": workload_name(args.config, sc), "sample": sample,
+                   "pixel_pulses_counted_by": "sum(kstop - kstart) from the oracle's own aperture "
+                                              "bounds at 8 range columns of the sample's first line, "
+                                              "times lines x width (apertures vary smoothly with "
+                                              "range and not with azimuth)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": oracle.kind,
                          "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -217,180 +235,263 @@ def estimate_pp(sc, a0, n):
     return total / len(cols) * width * n
 
 
-def run_ours(args):
-    rank, world, local = dist_env()
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist_mod
-        torch.cuda.set_device(local)
-        dist_mod.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
-        dist = dist_mod
-    from isce3_b200 import focus
-    from isce3_b200.focus import BackprojectPlan, backproject, last_stats, measure_peaks
+class Comm:
+    """torch.distributed plumbing of the bench (NCCL for the timing reductions, a gloo group
+    for host-only barriers); a no-op at N = 1."""
 
-    t_gen = time.perf_counter()
-    sc = make_scene(args)
-    t_gen = time.perf_counter() - t_gen
-    og = sc.out_geometry
-    a0, a1 = block_bounds(og.grid_length, world, rank)
-    sub = sc.out_subgrid(a0, a1) if world > 1 else og
-    shape = (a1 - a0, og.grid_width)
-    taps = int(np.ceil(sc.kernel.width))
-    common = (sc.in_geometry, sc.dem, sc.fc, sc.ds, sc.kernel, sc.dry_tropo_model,
-              sc.rdr2geo_params, sc.geo2rdr_params)
+    def __init__(self, rank, world, local):
+        self.rank, self.world, self.local = rank, world, local
+        self.dist = None
+        self.cpu_group = None
+        if world > 1:
+            import torch
+            import torch.distributed as dist_mod
+            torch.cuda.set_device(local)
+            dist_mod.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+            self.dist = dist_mod
+            self.cpu_group = dist_mod.new_group(backend="gloo")
 
-    def barrier():
-        if dist is not None:
+    def barrier(self):
+        if self.dist is not None:
             import torch
             torch.cuda.synchronize()
-            dist.barrier()
+            self.dist.barrier()
 
-    def max_over_ranks(x):
-        if dist is None:
+    def host_barrier(self):
+        """No GPU work on any rank (an NCCL barrier would spin kernels on the waiting GPUs)."""
+        if self.dist is not None:
+            self.dist.barrier(group=self.cpu_group)
+
+    def _reduce(self, x, op):
+        if self.dist is None:
             return x
         import torch
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        self.dist.all_reduce(t, op=op)
         return float(t.item())
 
-    def sum_over_ranks(x):
-        if dist is None:
-            return x
-        import torch
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    def max(self, x):
+        return self._reduce(x, self.dist.ReduceOp.MAX) if self.dist else x
 
-    peaks = measure_peaks(local)
+    def sum(self, x):
+        return self._reduce(x, self.dist.ReduceOp.SUM) if self.dist else x
 
-    # host buffers for the end-to-end arm: pinned when torch is importable
-    rc_host = sc.rc
-    pinned_note = "pageable"
-    try:
-        import torch
-        pin = torch.empty(sc.rc.shape, dtype=torch.complex64, pin_memory=True)
-        pin_np = pin.numpy()
-        pin_np[...] = sc.rc
-        rc_host = pin_np
-        pinned_note = "pinned"
-        out_pin = torch.empty(shape, dtype=torch.complex64, pin_memory=True)
-        out_host = out_pin.numpy()
-    except Exception:
-        out_host = np.empty(shape, np.complex64)
+    def close(self):
+        if self.dist is not None:
+            self.dist.destroy_process_group()
 
-    # ---- resident arm -------------------------------------------------------------
-    plan = BackprojectPlan(sub, sc.rc, *common, batch=args.batch, devices=[local])
-    for _ in range(args.warmup):
+
+def host_buffers(sc, shape, want_pinned=True):
+    """(rc_host, out_host, kind): pinned through torch when available, else pageable numpy."""
+    if want_pinned:
+        try:
+            import torch
+            pin = torch.empty(sc.rc.shape, dtype=torch.complex64, pin_memory=True)
+            rc_host = pin.numpy()
+            rc_host[...] = sc.rc
+            out_pin = torch.empty(shape, dtype=torch.complex64, pin_memory=True)
+            return rc_host, out_pin.numpy(), "pinned", (pin, out_pin)
+        except Exception:
+            pass
+    return sc.rc, np.empty(shape, np.complex64), "pageable", None
+
+
+def measure(comm, sc, steps, warmup, batch, sampler=None, e2e_steps=None, pinned=True):
+    """Resident and end-to-end timing of one frame at this N.  Returns a dict; the image of
+    this rank's block is under "img" (popped by the caller)."""
+    from isce3_b200.focus import BackprojectPlan, backproject, last_stats
+    og = sc.out_geometry
+    a0, a1 = block_bounds(og.grid_length, comm.world, comm.rank)
+    sub = sc.out_subgrid(a0, a1) if comm.world > 1 else og
+    shape = (a1 - a0, og.grid_width)
+    common = (sc.in_geometry, sc.dem, sc.fc, sc.ds, sc.kernel, sc.dry_tropo_model,
+              sc.rdr2geo_params, sc.geo2rdr_params)
+    rc_host, out_host, host_kind, keep = host_buffers(sc, shape, pinned)
+
+    plan = BackprojectPlan(sub, sc.rc, *common, batch=batch, devices=[comm.local])
+    for _ in range(warmup):
         plan.execute()
-    sampler = ClockSampler(local)
-    if rank == 0:
+    if sampler is not None:
         sampler.start()
-    barrier()
-    kernel_ms, solve_ms, launches = 0.0, 0.0, 0
+    comm.barrier()
+    kernel_ms = solve_ms = 0.0
+    launches = 0
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         plan.execute()
         st = plan.stats()
         kernel_ms += st["ms_accumulate"]
         solve_ms += st["ms_target_solve"]
         launches += st["total_launches"]
-    barrier()
-    elapsed = time.perf_counter() - t0
-    clocks = sampler.stop() if rank == 0 else None
+    comm.barrier()
+    elapsed = comm.max(time.perf_counter() - t0)
+    clocks = sampler.stop() if sampler is not None else None
     st = plan.stats()
-    elapsed = max_over_ranks(elapsed)
     pp_rank = st["pixel_pulses"]
-    pp_total = sum_over_ranks(pp_rank)
-    ms_per_step = 1e3 * elapsed / args.steps
-    value = pp_total / (ms_per_step * 1e-3)
-    kernel_ms_step = kernel_ms / args.steps
+    pp_total = comm.sum(pp_rank)
+    ms_per_step = 1e3 * elapsed / steps
     img = plan.download()
     plan.close()
 
     # ---- end-to-end arm: host buffers through the reference-shaped call ---------------
-    for _ in range(min(args.warmup, 3)):
-        backproject(out_host, sub, rc_host, *common, batch=args.batch, devices=[local])
-    barrier()
+    e2e_steps = e2e_steps or steps
+    for _ in range(min(warmup, 3)):
+        backproject(out_host, sub, rc_host, *common, batch=batch, devices=[comm.local])
+    comm.barrier()
     t0 = time.perf_counter()
     h2d = d2h = 0
-    e2e_launches = 0
-    for _ in range(args.steps):
-        backproject(out_host, sub, rc_host, *common, batch=args.batch, devices=[local])
+    for _ in range(e2e_steps):
+        backproject(out_host, sub, rc_host, *common, batch=batch, devices=[comm.local])
         s2 = last_stats()
         h2d, d2h = s2["h2d_bytes"], s2["d2h_bytes"]
-        e2e_launches += s2["total_launches"]
-    barrier()
-    e2e_elapsed = max_over_ranks(time.perf_counter() - t0)
-    e2e_value = pp_total / (e2e_elapsed / args.steps)
+    comm.barrier()
+    e2e_elapsed = comm.max(time.perf_counter() - t0)
     same = float(np.nanmax(np.abs(out_host - img))) if img.size else 0.0
-
-    if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return 0
-
-    flops_pp = algorithmic_flops_per_pp(taps)
-    achieved_tflops = flops_pp * pp_rank / (kernel_ms_step * 1e-3) / 1e12 if kernel_ms_step > 0 else 0.0
-    nominal_fp32 = 148 * 128 * 2 * 1965e6 / 1e12
-    peaks_file = {}
-    try:
-        peaks_file = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
-    except Exception:
-        pass
-    ig = sc.in_geometry
-    alg_bytes = 8.0 * (st["pulse_last"] - st["pulse_first"]) * ig.grid_width + 8.0 * shape[0] * shape[1] \
-        + 40.0 * shape[0] * shape[1]
-    roofline = {
-        "bound": "fp32", "kernel": f"accumulate_fast_kernel<{taps}>" if st["used_fast_kernel"] else "accumulate_generic_kernel",
-        "achieved": achieved_tflops, "peak": peaks["fp32_tflops"], "unit": "TFLOP/s",
-        "frac": achieved_tflops / peaks["fp32_tflops"] if peaks["fp32_tflops"] else None,
-        "peak_source": "i3b_measure_peaks FFMA microbenchmark on this device (MEASURED_PEAKS.json has no FP32 peak)",
-        "frac_of_nominal_74.5": achieved_tflops / nominal_fp32,
-        "flops_per_pixel_pulse": flops_pp, "kernel_ms_per_step": kernel_ms_step,
-        "kernel_share_of_step": kernel_ms_step / ms_per_step,
-        "pp_per_s_kernel": pp_rank / (kernel_ms_step * 1e-3) if kernel_ms_step > 0 else None,
-        "sfu_frac": (3.0 * pp_rank / (kernel_ms_step * 1e-3) / 1e9) / peaks["sfu_gops"] if kernel_ms_step > 0 else None,
-        "hbm_algorithmic_gbs": alg_bytes / (kernel_ms_step * 1e-3) / 1e9 if kernel_ms_step > 0 else None,
-        "hbm_peak_gbs": peaks_file.get("hbm_gbs"),
-        "measured_peaks": peaks, "traffic": None,
+    taps = int(np.ceil(sc.kernel.width))
+    kms = kernel_ms / steps
+    return {
+        "value": pp_total / (ms_per_step * 1e-3), "ms_per_step": ms_per_step, "pp_total": pp_total,
+        "pp_rank": pp_rank, "kernel_ms_step": kms, "solve_ms_step": solve_ms / steps,
+        "launches": launches, "clocks": clocks, "stats": st, "taps": taps, "shape": shape,
+        "block": (a0, a1), "sub": sub, "common": common, "rc_host": rc_host, "out_host": out_host,
+        "host_kind": host_kind, "_keep": keep, "img": img,
+        "e2e": {"value": pp_total / (e2e_elapsed / e2e_steps), "unit": UNIT,
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "host_memory": host_kind, "ms_per_step": 1e3 * e2e_elapsed / e2e_steps,
+                "max_abs_diff_vs_resident": same},
+        "achieved_tflops": algorithmic_flops_per_pp(taps) * pp_rank / (kms * 1e-3) / 1e12 if kms > 0 else 0.0,
     }
-    # DRAM traffic of the dominant kernel: one ncu capture of this workload, committed under
-    # profiles/ (per launch, like `achieved`); only quoted for the workload it was taken on
-    try:
-        tr = json.loads((ROOT / "profiles" / "r01_traffic.json").read_text())
-        if world == 1 and args.config == "c2" and args.scale == 1.0 and not args.taps:
-            roofline["traffic"] = tr["dram_bytes_read"] + tr["dram_bytes_write"]
-            roofline["traffic_unit"] = "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)"
-            roofline["traffic_source"] = tr["source"]
-            roofline["algorithmic_bytes_per_launch"] = alg_bytes + 32.0 * shape[0] * shape[1]
-    except Exception:
-        pass
 
-    cpu = None
-    if not args.no_cpu:
+
+def cpu_parity(comm, sc, m, oracle, cores, budget_pp=2.5e8):
+    """CPU oracle on a bounded sample inside this rank's block; returns (cpu dict, parity)."""
+    og = sc.out_geometry
+    a0, a1 = m["block"]
+    shape = m["shape"]
+    ppx = m["pp_rank"] / max(shape[0] * shape[1], 1)
+    lines = max(1, int(budget_pp * cores / 8 / max(ppx * og.grid_width, 1)))
+    lines = min(lines, shape[0])
+    # sample centred in this rank's block
+    c = (a0 + a1) // 2
+    b0 = max(a0, min(c - lines // 2, a1 - lines))
+    sub = sc.out_subgrid(b0, b0 + lines)
+    ref = np.zeros((lines, og.grid_width), np.complex64)
+    t = time.perf_counter()
+    oracle.backproject(ref, sub, sc.rc, sc.in_geometry, sc.dem, sc.fc, sc.ds, sc.kernel,
+                       sc.dry_tropo_model, sc.rdr2geo_params, sc.geo2rdr_params)
+    dt = time.perf_counter() - t
+    g = m["img"][b0 - a0:b0 - a0 + lines]
+    ok = np.isfinite(ref)
+    parity = float(np.linalg.norm((g - ref)[ok]) / max(np.linalg.norm(ref[ok]), 1e-30))
+    pp_cpu = ppx * lines * og.grid_width
+    return {"value": pp_cpu / dt, "unit": UNIT, "cores": cores, "kind": oracle.kind,
+            "sample": f"{lines} azimuth lines x {og.grid_width} range pixels at the centre of rank 0's block "
+                      f"({pp_cpu:.3g} pixel*pulses, {dt:.1f} s)",
+            "rel_rms_gpu_vs_cpu_on_sample": parity}, parity
+
+
+def run_ours(args):
+    rank, world, local = dist_env()
+    comm = Comm(rank, world, local)
+    from isce3_b200 import focus
+    from isce3_b200.focus import backproject, last_stats, measure_peaks, release_device_memory
+
+    peaks = measure_peaks(local)
+    cores = os.cpu_count() or 1
+    oracle = None
+    if rank == 0 and not args.no_cpu:
         from oracle import tdbp
-        cores = os.cpu_count() or 1
         tdbp.set_threads(cores)  # torchrun exports OMP_NUM_THREADS=1 to its workers
         oracle = tdbp.best()
+
+    t_gen = time.perf_counter()
+    sc = make_scene(args.config, args.scale, args.taps)
+    t_gen = time.perf_counter() - t_gen
+    og = sc.out_geometry
+    in_width = sc.in_geometry.grid_width
+    sampler = ClockSampler(local) if rank == 0 else None
+    m = measure(comm, sc, args.steps, args.warmup, args.batch, sampler)
+    st, taps, shape = m["stats"], m["taps"], m["shape"]
+    pp_rank, kernel_ms_step = m["pp_rank"], m["kernel_ms_step"]
+    rc_host, out_host, sub, common = m["rc_host"], m["out_host"], m["sub"], m["common"]
+
+    # ---- the general (non-baked coefficient) kernel on the same frame ------------------
+    roofline_general = None
+    if st["used_fast_kernel"] and st["fast_variant"] >= 0:
+        os.environ["I3B_FAST_NO_IMM"] = "1"
+        try:
+            g = measure_resident_only(comm, sc, 2, 1, args.batch)
+        finally:
+            del os.environ["I3B_FAST_NO_IMM"]
+        if rank == 0:
+            ach = algorithmic_flops_per_pp(taps) * g["pp_rank"] / (g["kernel_ms_step"] * 1e-3) / 1e12
+            roofline_general = {"kernel": f"accumulate_fast_kernel<{taps}, CoefBank> (coefficients from shared memory)",
+                                "fast_variant": g["fast_variant"], "achieved": ach, "unit": "TFLOP/s",
+                                "frac": ach / peaks["fp32_tflops"], "kernel_ms_per_step": g["kernel_ms_step"],
+                                "value": g["value"]}
+
+    # ---- end to end from pageable host memory (what the workflow passes) -----------------
+    e2e_pageable = None
+    if not args.no_extras:
+        out_pg = np.empty(shape, np.complex64)
+        h_pg = np.empty(shape, np.float32)
+        backproject(out_pg, sub, sc.rc, *common, batch=args.batch, devices=[local], height=h_pg)
+        comm.barrier()
+        t0 = time.perf_counter()
+        n_pg = 2
+        for _ in range(n_pg):
+            backproject(out_pg, sub, sc.rc, *common, batch=args.batch, devices=[local], height=h_pg)
+        comm.barrier()
+        dt = comm.max(time.perf_counter() - t0)
+        e2e_pageable = {"value": m["pp_total"] / (dt / n_pg), "unit": UNIT, "ms_per_step": 1e3 * dt / n_pg,
+                        "host_memory": "pageable in, pageable out and height (numpy arrays)",
+                        "bit_identical_to_resident": bool(np.array_equal(out_pg, m["img"]))}
+        del out_pg, h_pg
+
+    # ---- in-library multi-GPU driver: one process, one pageable in / out ------------------
+    inlib = None
+    if world > 1 and not args.no_extras:
+        release_device_memory()
+        comm.host_barrier()
+        if rank == 0:
+            full = np.empty((og.grid_length, og.grid_width), np.complex64)
+            devs = list(range(world))
+            full_args = (og, sc.rc) + common
+            backproject(full, *full_args, batch=args.batch, devices=devs)
+            t0 = time.perf_counter()
+            n_il = 3
+            for _ in range(n_il):
+                backproject(full, *full_args, batch=args.batch, devices=devs)
+            dt = (time.perf_counter() - t0) / n_il
+            s2 = last_stats()
+            a0, a1 = m["block"]
+            inlib = {"value": s2["pixel_pulses"] / dt, "unit": UNIT, "ms_per_step": 1e3 * dt,
+                     "n_devices": s2["n_devices"], "h2d_bytes_per_step": int(s2["h2d_bytes"]),
+                     "d2h_bytes_per_step": int(s2["d2h_bytes"]),
+                     "what": "rank 0 alone: backproject(out, ..., devices=[0..N-1]) on the whole frame, "
+                             "ONE pageable input array, ONE pageable output array, one host thread per device",
+                     "vs_torchrun_e2e": (s2["pixel_pulses"] / dt) / m["e2e"]["value"],
+                     "rank0_block_bit_identical_to_torchrun": bool(np.array_equal(full[a0:a1], m["img"]))}
+            del full
+            release_device_memory()
+        comm.host_barrier()
+
+    cpu = None
+    if rank == 0 and oracle is not None:
+        cpu, _ = cpu_parity(comm, sc, m, oracle, cores)
+        # one-thread figure on a proportionally smaller sample (BASELINE.md section 3)
+        from oracle import tdbp
+        tdbp.set_threads(1)
         ppx = pp_rank / max(shape[0] * shape[1], 1)
-        lines = max(1, int(2.5e8 * cores / 8 / max(ppx * og.grid_width, 1)))
-        dt, b0, n, ref = cpu_sample(sc, oracle, lines)
-        pp_cpu = ppx * n * og.grid_width
-        lo = b0 - a0
-        parity = None
-        if world == 1:
-            g = img[lo:lo + n]
-            m = np.isfinite(ref)
-            parity = float(np.linalg.norm((g - ref)[m]) / max(np.linalg.norm(ref[m]), 1e-30))
-        cpu = {"value": pp_cpu / dt, "unit": UNIT, "cores": cores, "kind": oracle.kind,
-               "sample": f"{n} azimuth lines x {og.grid_width} range pixels at the frame centre "
-                         f"({pp_cpu:.3g} pixel*pulses, {dt:.1f} s)",
-               "rel_rms_gpu_vs_cpu_on_sample": parity}
+        cols = max(64, min(og.grid_width, int(6e7 / max(ppx, 1))))
+        dt1, _, _, _ = cpu_sample(sc, oracle, 1, cols)
+        cpu["value_1_thread"] = ppx * cols / dt1
+        cpu["sample_1_thread"] = f"1 azimuth line x {cols} range pixels ({ppx * cols:.3g} pixel*pulses, {dt1:.1f} s)"
+        tdbp.set_threads(cores)
 
     # ---- same-GPU comparator: the reference's own CUDA backprojection (reduced harness) ---
     ref_cuda = None
-    if not args.no_ref_cuda and world == 1:
+    if rank == 0 and not args.no_ref_cuda and world == 1:
         try:
             from oracle import tdbp
             if tdbp.have_ref_cuda() and not sc.dem.have_raster:
@@ -402,15 +503,16 @@ def run_ours(args):
                 t0 = time.perf_counter()
                 rcu.backproject(ref_out, sub, rc_host, *common, batch=args.batch)
                 dt = time.perf_counter() - t0
-                m = np.isfinite(ref_out) & np.isfinite(out_host)
+                ok = np.isfinite(ref_out) & np.isfinite(out_host)
                 ref_cuda = {
                     "value": pp_rank / dt, "unit": UNIT, "ms": 1e3 * dt, "kind": rcu.kind,
                     "what": "isce3::cuda::focus::backproject (cuda/focus/Backproject.cu, unmodified) "
                             "on the same frame, same host buffers, one call, wall time",
-                    "e2e_speedup_of_this_repo": e2e_value / (pp_rank / dt),
+                    "e2e_speedup_of_this_repo": m["e2e"]["value"] / (pp_rank / dt),
                     "rel_rms_ours_vs_reference_cuda": float(
-                        np.linalg.norm((out_host - ref_out)[m]) / max(np.linalg.norm(ref_out[m]), 1e-30)),
+                        np.linalg.norm((out_host - ref_out)[ok]) / max(np.linalg.norm(ref_out[ok]), 1e-30)),
                 }
+                del ref_out
             elif sc.dem.have_raster:
                 ref_cuda = {"unavailable": "reduced harness supports constant-height DEMs only"}
             else:
@@ -418,29 +520,181 @@ def run_ours(args):
         except Exception as exc:  # the comparator must never take the bench down
             ref_cuda = {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
 
+    # ---- slowest supported path: the generic kernel (kernels / shapes the fast path refuses) ---
+    worst = None
+    if rank == 0 and not args.no_extras:
+        try:
+            worst = measure_generic(sc, local, args.batch)
+            if ref_cuda and "value" in ref_cuda:
+                worst["reference_cuda_pp_s_same_box"] = ref_cuda["value"]
+        except Exception as exc:
+            worst = {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
+
+    main_workload = workload_name(args.config, sc)
+    main_img_free = m.pop("img")
+    del main_img_free, rc_host, out_host
+    m["_keep"] = None
+    m["rc_host"] = m["out_host"] = None
+
+    # ---- every other BASELINE.json shape at this N (a few steps each) ----------------------
+    configs = {}
+    if not args.no_extras and args.scale == 1.0 and args.config == "c2" and not args.taps:
+        del sc
+        gc.collect()
+        release_device_memory()
+        for name, cfg, taps_list in (("c1", "c1", [0]), ("c4", "c4", [0]), ("c5", "c5", [8, 16, 32])):
+            try:
+                scx = make_scene(cfg, 1.0, taps_list[0], **({"n_targets": 81} if cfg == "c4" else {}))
+            except Exception as exc:
+                configs[name] = {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
+                continue
+            for tp in taps_list:
+                key = name if not tp else f"{name}k{tp}"
+                try:
+                    if tp:
+                        from testkit import synth
+                        scx.kernel = synth.knab_table_kernel(tp, 0.8, 2048)
+                    mx = measure(comm, scx, 2, 1, args.batch, None, pinned=True)
+                    entry = None
+                    if rank == 0:
+                        entry = {"workload": workload_name(cfg, scx), "value": mx["value"], "unit": UNIT,
+                                 "ms_per_step": mx["ms_per_step"],
+                                 "e2e": {k: mx["e2e"][k] for k in ("value", "ms_per_step", "h2d_bytes_per_step",
+                                                                   "d2h_bytes_per_step", "host_memory")},
+                                 "e2e_bit_identical_to_resident": mx["e2e"]["max_abs_diff_vs_resident"] == 0.0,
+                                 "roofline_frac": mx["achieved_tflops"] / peaks["fp32_tflops"],
+                                 "achieved_tflops": mx["achieved_tflops"],
+                                 "kernel_ms_per_step": mx["kernel_ms_step"],
+                                 "target_solve_ms_per_step": mx["solve_ms_step"],
+                                 "fast_variant": mx["stats"]["fast_variant"],
+                                 "used_fast_kernel": mx["stats"]["used_fast_kernel"],
+                                 "pixel_pulses_per_step": mx["pp_total"]}
+                        if oracle is not None:
+                            c, parity = cpu_parity(comm, scx, mx, oracle, cores, budget_pp=1.0e8)
+                            entry["rel_rms_vs_cpu_reference_on_sample"] = parity
+                            entry["cpu_reference_pp_s"] = c["value"]
+                            entry["cpu_sample"] = c["sample"]
+                        configs[key] = entry
+                    mx.clear()
+                except Exception as exc:
+                    if rank == 0:
+                        configs[key] = {"unavailable": f"{type(exc).__name__}: {exc}"[:300]}
+            del scx
+            gc.collect()
+            release_device_memory()
+
+    if rank != 0:
+        comm.close()
+        return 0
+
+    achieved_tflops = m["achieved_tflops"]
+    peaks_file = {}
+    try:
+        peaks_file = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        pass
+    npulse_used = st["pulse_last"] - st["pulse_first"]
+    alg_bytes = 8.0 * npulse_used * in_width + 8.0 * shape[0] * shape[1] + 40.0 * shape[0] * shape[1]
+    roofline = {
+        "bound": "fp32", "kernel": f"accumulate_fast_kernel<{taps}>" if st["used_fast_kernel"] else "accumulate_generic_kernel",
+        "fast_variant": st["fast_variant"],
+        "achieved": achieved_tflops, "peak": peaks["fp32_tflops"], "unit": "TFLOP/s",
+        "frac": achieved_tflops / peaks["fp32_tflops"] if peaks["fp32_tflops"] else None,
+        "peak_source": "i3b_measure_peaks FFMA microbenchmark on this device (MEASURED_PEAKS.json has no FP32 peak)",
+        "frac_of_nominal_74.5": achieved_tflops / NOMINAL_FP32_TFLOPS,
+        "flops_per_pixel_pulse": algorithmic_flops_per_pp(taps), "kernel_ms_per_step": kernel_ms_step,
+        "kernel_share_of_step": kernel_ms_step / m["ms_per_step"],
+        "pp_per_s_kernel": pp_rank / (kernel_ms_step * 1e-3) if kernel_ms_step > 0 else None,
+        "sfu_frac": (3.0 * pp_rank / (kernel_ms_step * 1e-3) / 1e9) / peaks["sfu_gops"] if kernel_ms_step > 0 else None,
+        "hbm_algorithmic_gbs": alg_bytes / (kernel_ms_step * 1e-3) / 1e9 if kernel_ms_step > 0 else None,
+        "hbm_peak_gbs": peaks_file.get("hbm_gbs"),
+        "measured_peaks": peaks, "traffic": None,
+    }
+    # DRAM traffic of the dominant kernel: one ncu capture of this workload, committed under
+    # profiles/ (per launch, like `achieved`); only quoted for the workload it was taken on
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            tr = json.loads((ROOT / "profiles" / name).read_text())
+            if world == 1 and args.config == "c2" and args.scale == 1.0 and not args.taps:
+                roofline["traffic"] = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+                roofline["traffic_unit"] = "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)"
+                roofline["traffic_source"] = tr["source"]
+                roofline["algorithmic_bytes_per_launch"] = alg_bytes + 32.0 * shape[0] * shape[1]
+            break
+        except Exception:
+            continue
+    # roofline fractions of the wide / narrow kernels measured in `configs`
+    by_taps = {f"k{taps}": roofline["frac"]}
+    for key, entry in configs.items():
+        if key.startswith("c5k") and "roofline_frac" in entry:
+            by_taps[key[2:]] = entry["roofline_frac"]
+    roofline["frac_by_taps"] = by_taps
+
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "metric": METRIC, "value": m["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": m["ms_per_step"], "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64+f32", "data": "synthetic",
-        "config": {"workload": workload_name(args, sc), "sharding": "contiguous azimuth blocks of one frame, no exchange",
+        "config": {"workload": main_workload, "sharding": "contiguous azimuth blocks of one frame, no exchange",
                    "l2": "inputs (swath + per-pixel tables) far exceed the 126 MB L2",
-                   "pixel_pulses_per_step": pp_total, "batch": args.batch,
+                   "pixel_pulses_per_step": m["pp_total"], "batch": args.batch,
                    "scene_generation_s": t_gen},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(d2h), "host_memory": pinned_note,
-                "ms_per_step": 1e3 * e2e_elapsed / args.steps,
-                "max_abs_diff_vs_resident": same},
-        "gpu_launches": int(launches),
-        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "reference_cuda": ref_cuda,
-        "target_solve_ms_per_step": solve_ms / args.steps,
+        "e2e": m["e2e"], "e2e_pageable": e2e_pageable,
+        "gpu_launches": int(m["launches"]),
+        "clocks": m["clocks"], "roofline": roofline, "roofline_general": roofline_general,
+        "cpu_baseline": cpu, "reference_cuda": ref_cuda,
+        "worst_supported_path": worst, "inlib_multi_gpu": inlib, "configs": configs,
+        "target_solve_ms_per_step": m["solve_ms_step"],
         # CUDA-event time of the two kernels that make up a resident step (rank 0); the
         # difference to ms_per_step (wall, barrier to barrier) is finalisation + host overhead
-        "device_ms_per_step": kernel_ms_step + solve_ms / args.steps,
+        "device_ms_per_step": kernel_ms_step + m["solve_ms_step"],
     }
     print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
+    comm.close()
     return 0
+
+
+def measure_resident_only(comm, sc, steps, warmup, batch):
+    from isce3_b200.focus import BackprojectPlan
+    og = sc.out_geometry
+    a0, a1 = block_bounds(og.grid_length, comm.world, comm.rank)
+    sub = sc.out_subgrid(a0, a1) if comm.world > 1 else og
+    plan = BackprojectPlan(sub, sc.rc, sc.in_geometry, sc.dem, sc.fc, sc.ds, sc.kernel, sc.dry_tropo_model,
+                           sc.rdr2geo_params, sc.geo2rdr_params, batch=batch, devices=[comm.local])
+    for _ in range(warmup):
+        plan.execute()
+    comm.barrier()
+    kms = 0.0
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        plan.execute()
+        st = plan.stats()
+        kms += st["ms_accumulate"]
+    comm.barrier()
+    el = comm.max(time.perf_counter() - t0)
+    pp_total = comm.sum(st["pixel_pulses"])
+    plan.close()
+    return {"value": pp_total / (el / steps), "kernel_ms_step": kms / steps, "pp_rank": st["pixel_pulses"],
+            "fast_variant": st["fast_variant"]}
+
+
+def measure_generic(sc, local, batch):
+    """The generic accumulation kernel (exact kernel evaluation, any kernel type / tap count /
+    output spacing) on a block of the same frame: the slowest path a supported call can take."""
+    from isce3_b200.focus import BackprojectPlan
+    og = sc.out_geometry
+    n = min(og.grid_length, 256)
+    a0 = max(0, og.grid_length // 2 - n // 2)
+    sub = sc.out_subgrid(a0, a0 + n)
+    plan = BackprojectPlan(sub, sc.rc, sc.in_geometry, sc.dem, sc.fc, sc.ds, sc.kernel, sc.dry_tropo_model,
+                           sc.rdr2geo_params, sc.geo2rdr_params, batch=batch, devices=[local],
+                           force_generic=True)
+    plan.execute()
+    plan.execute()
+    st = plan.stats()
+    plan.close()
+    return {"kernel": "accumulate_generic_kernel (force_generic)", "value": st["pixel_pulses"] / (st["ms_accumulate"] * 1e-3),
+            "unit": UNIT, "kernel_ms": st["ms_accumulate"],
+            "sample": f"{n} azimuth lines x {og.grid_width} range pixels of the frame ({st['pixel_pulses']:.3g} pixel*pulses)"}
 
 
 def main():
@@ -456,6 +710,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true",
                     help="skip the reference-CUDA comparator (one ~8 s call at C2)")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="main workload only: no other configs, pageable / in-library / generic arms")
     args = ap.parse_args()
     args.warmup_ref = min(args.warmup, 1)
     if args.impl == "reference":

@@ -287,6 +287,9 @@ typedef struct {
     double max_err;
     float even[I3B_FIT_MAX_TAP_PAIRS][I3B_FIT_MAX_COEF];
     float odd[I3B_FIT_MAX_TAP_PAIRS][I3B_FIT_MAX_COEF];
+    int32_t pair_degree[I3B_FIT_MAX_TAP_PAIRS]; /* degree used for tap pair m (<= degree):
+                            outer pairs carry small weights and need fewer terms       */
+    int32_t _pad;
 } I3B_TapPolyFit;
 
 /* ---- entry points -------------------------------------------------------- */

@@ -226,6 +226,8 @@ class TapPolyFit(C.Structure):
         ("max_err", C.c_double),
         ("even", (C.c_float * FIT_MAX_COEF) * FIT_MAX_TAP_PAIRS),
         ("odd", (C.c_float * FIT_MAX_COEF) * FIT_MAX_TAP_PAIRS),
+        ("pair_degree", C.c_int32 * FIT_MAX_TAP_PAIRS),
+        ("_pad", C.c_int32),
     ]
 
 

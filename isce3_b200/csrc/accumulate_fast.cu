@@ -248,16 +248,23 @@ __device__ __forceinline__ double2 lds_d2(uint32_t addr)
 // constant-bank operand form).  CoefImm<V> reads a build-time table (tap_poly_imm.h): after
 // unrolling every coefficient is an FFMA2 immediate -- no loads at all.  The launcher picks
 // CoefImm<V> only when the run-time fit of the caller's kernel equals table V.
+// Degrees are per tap PAIR (the host fit gives outer pairs, whose weights are small, the
+// lowest degree that meets its tolerance): a baked table knows each pair's degree at compile
+// time and evaluates no more terms than that; the general kernel runs every pair at the
+// maximum degree with zeros for the missing leading coefficients -- fma(0, h, c) == c, so
+// both produce bit-identical weights.
 struct CoefBank {
     static constexpr bool kImm = false;
     __device__ static __forceinline__ float e(int, int) { return 0.f; } // (rows come through Top::bank)
     __device__ static __forceinline__ float o(int, int) { return 0.f; }
+    __host__ __device__ static constexpr int deg(int, int dmax) { return dmax; }
 };
 template<int V>
 struct CoefImm {
     static constexpr bool kImm = true;
     __device__ static __forceinline__ constexpr float e(int m, int i) { return imm::Table<V>::even(m, i); }
     __device__ static __forceinline__ constexpr float o(int m, int i) { return imm::Table<V>::odd(m, i); }
+    __host__ __device__ static constexpr int deg(int m, int) { return imm::Table<V>::deg(m); }
 };
 
 #ifndef I3B_HOIST_TOP
@@ -265,8 +272,11 @@ struct CoefImm {
 #endif
 template<int K, int D, class Coef>
 struct Weights {
-    static constexpr int NE = D / 2 + 1;       // even coefficients  f^0, f^2, ...
+    static constexpr int NE = D / 2 + 1;       // even coefficients  f^0, f^2, ...   (maximum degree)
     static constexpr int NO = (D + 1) / 2;     // odd coefficients   f^1, f^3, ...
+    // per tap pair
+    __host__ __device__ static constexpr int ne(int m) { return Coef::deg(m, D) / 2 + 1; }
+    __host__ __device__ static constexpr int no(int m) { return (Coef::deg(m, D) + 1) / 2; }
     static constexpr bool kHoist = Coef::kImm && I3B_HOIST_TOP;
     // Leading coefficients.  An FFMA2 takes ONE immediate, so the first Horner step
     // (c_top * h + c_next) needs c_top in a register; left to itself ptxas re-creates these
@@ -285,17 +295,17 @@ struct Weights {
         if (kHoist) {
 #pragma unroll
             for (int m = 0; m < (K + 1) / 2; ++m)
-                t.e[m] = __int_as_float(__float_as_int(Coef::e(m, NE - 1)) + zero);
+                t.e[m] = __int_as_float(__float_as_int(Coef::e(m, ne(m) - 1)) + zero);
 #pragma unroll
             for (int m = 0; m < K / 2; ++m)
-                t.o[m] = __int_as_float(__float_as_int(Coef::o(m, NO - 1)) + zero);
+                t.o[m] = __int_as_float(__float_as_int(Coef::o(m, no(m) - 1)) + zero);
         }
     }
-    // One tap pair: wlo = w_m(f), whi = w_{K-1-m}(f) of both pixels, from h = f*f, nf = -f.
+    // even / odd parts of tap pair m at h = f * f (both pixels)
     template<int m>
-    __device__ static __forceinline__ void pair(f32x2 f, f32x2 h, f32x2 nf, f32x2& wlo, f32x2& whi,
-                                                const Top& top)
+    __device__ static __forceinline__ void parts(f32x2 h, f32x2& e, f32x2& o, const Top& top)
     {
+        constexpr int ne_ = ne(m), no_ = no(m);
         float cev[4], cov[4];
         if (Coef::kImm) {
 #pragma unroll
@@ -304,74 +314,64 @@ struct Weights {
                 cov[i] = Coef::o(m, i);
             }
             if (kHoist) {
-                cev[NE - 1] = top.e[m];
-                cov[NO - 1] = top.o[m];
+                cev[ne_ - 1] = top.e[m];
+                if (2 * m != K - 1) cov[no_ - 1] = top.o[m < K / 2 ? m : 0];
             }
         } else {
             // broadcast LDS.128 (all lanes the same address): they issue in the FFMA2 shadow
-            const float4 ce = lds128(top.bank + 32u * m), co = lds128(top.bank + 32u * m + 16u);
+            const float4 ce = lds128(top.bank + 32u * m);
             cev[0] = ce.x; cev[1] = ce.y; cev[2] = ce.z; cev[3] = ce.w;
-            cov[0] = co.x; cov[1] = co.y; cov[2] = co.z; cov[3] = co.w;
+            if (2 * m != K - 1) {
+                const float4 co = lds128(top.bank + 32u * m + 16u);
+                cov[0] = co.x; cov[1] = co.y; cov[2] = co.z; cov[3] = co.w;
+            } else {
+                cov[0] = cov[1] = cov[2] = cov[3] = 0.f;
+            }
         }
-        f32x2 e = bcast2(cev[NE - 1]);
+        e = bcast2(cev[ne_ - 1]);
 #pragma unroll
-        for (int i = NE - 2; i >= 0; --i) e = fma2(e, h, bcast2(cev[i]));
-        f32x2 o = bcast2(cov[NO - 1]);
+        for (int i = ne_ - 2; i >= 0; --i) e = fma2(e, h, bcast2(cev[i]));
+        o = bcast2(cov[no_ - 1]);
+        if (2 * m != K - 1) {
 #pragma unroll
-        for (int i = NO - 2; i >= 0; --i) o = fma2(o, h, bcast2(cov[i]));
+            for (int i = no_ - 2; i >= 0; --i) o = fma2(o, h, bcast2(cov[i]));
+        }
+    }
+    // One tap pair: wlo = w_m(f), whi = w_{K-1-m}(f) of both pixels, from h = f*f, nf = -f.
+    template<int m>
+    __device__ static __forceinline__ void pair(f32x2 f, f32x2 h, f32x2 nf, f32x2& wlo, f32x2& whi,
+                                                const Top& top)
+    {
+        f32x2 e, o;
+        parts<m>(h, e, o, top);
         wlo = fma2(f, o, e);
         whi = fma2(nf, o, e);
+    }
+    // centre tap of an odd-length kernel (even polynomial only)
+    __device__ static __forceinline__ f32x2 center(f32x2 h, const Top& top)
+    {
+        f32x2 e, o;
+        parts<K / 2>(h, e, o, top);
+        return e;
     }
 
     // Tap weights of TWO pixels at once: f = (f_pixel0, f_pixel1) in [-0.5, 0.5);
     // w[m] = (w_m(f0), w_m(f1)).  Coefficients enter as scalar-broadcast operands.
+    template<int m = 0>
+    __device__ static __forceinline__ void eval_from(f32x2 f, f32x2 h, f32x2 nf, f32x2 (&w)[K], const Top& top)
+    {
+        if constexpr (m < K / 2) {
+            pair<m>(f, h, nf, w[m], w[K - 1 - m], top);
+            eval_from<m + 1>(f, h, nf, w, top);
+        } else if constexpr (K & 1) {
+            w[K / 2] = center(h, top);
+        }
+    }
     __device__ static __forceinline__ void eval(f32x2 f, f32x2 (&w)[K], const Top& top)
     {
         const f32x2 h = mul2(f, f);
         const f32x2 nf = mul2(f, bcast2(-1.0f));
-#pragma unroll
-        for (int m = 0; m < K / 2; ++m) {
-            float cev[4], cov[4];
-            if (Coef::kImm) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    cev[i] = Coef::e(m, i);
-                    cov[i] = Coef::o(m, i);
-                }
-                if (kHoist) {
-                    cev[NE - 1] = top.e[m];
-                    cov[NO - 1] = top.o[m];
-                }
-            } else {
-                const float4 ce = lds128(top.bank + 32u * m), co = lds128(top.bank + 32u * m + 16u);
-                cev[0] = ce.x; cev[1] = ce.y; cev[2] = ce.z; cev[3] = ce.w;
-                cov[0] = co.x; cov[1] = co.y; cov[2] = co.z; cov[3] = co.w;
-            }
-            f32x2 e = bcast2(cev[NE - 1]);
-#pragma unroll
-            for (int i = NE - 2; i >= 0; --i) e = fma2(e, h, bcast2(cev[i]));
-            f32x2 o = bcast2(cov[NO - 1]);
-#pragma unroll
-            for (int i = NO - 2; i >= 0; --i) o = fma2(o, h, bcast2(cov[i]));
-            w[m] = fma2(f, o, e);
-            w[K - 1 - m] = fma2(nf, o, e);
-        }
-        if (K & 1) {
-            constexpr int m = K / 2;
-            float cev[4];
-            if (Coef::kImm) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) cev[i] = Coef::e(m, i);
-                if (kHoist) cev[NE - 1] = top.e[m];
-            } else {
-                const float4 ce = lds128(top.bank + 32u * m);
-                cev[0] = ce.x; cev[1] = ce.y; cev[2] = ce.z; cev[3] = ce.w;
-            }
-            f32x2 e = bcast2(cev[NE - 1]);
-#pragma unroll
-            for (int i = NE - 2; i >= 0; --i) e = fma2(e, h, bcast2(cev[i]));
-            w[m] = e;
-        }
+        eval_from<0>(f, h, nf, w, top);
     }
 };
 
@@ -412,6 +412,27 @@ constexpr int KK_UNROLL = I3B_KK_UNROLL;
 static_assert(SEG % TK == 0, "a geometry segment is a whole number of staged pulse tiles");
 constexpr float MAGIC32 = 12582912.0f;         // 1.5 * 2^23: float -> nearest integer by addition
 constexpr int MAGIC32_BITS = 0x4B400000;
+
+// The per-pixel record is re-read at every geometry segment (64 pulses); with the L1
+// evict-last hint the CTA's 20 KB of records stay in the small L1 left beside the shared
+// memory carve-out instead of coming from L2 each time.
+#ifndef I3B_PIX_L1
+#define I3B_PIX_L1 1
+#endif
+__device__ __forceinline__ PixelRec load_pixel(const PixelRec* p)
+{
+#if I3B_PIX_L1
+    PixelRec q;
+    asm volatile("ld.global.nc.L1::evict_last.f64 %0, [%1];" : "=d"(q.x) : "l"(&p->x));
+    asm volatile("ld.global.nc.L1::evict_last.f64 %0, [%1];" : "=d"(q.y) : "l"(&p->y));
+    asm volatile("ld.global.nc.L1::evict_last.f64 %0, [%1];" : "=d"(q.z) : "l"(&p->z));
+    asm volatile("ld.global.nc.L1::evict_last.f64 %0, [%1];" : "=d"(q.tau_atm) : "l"(&p->tau_atm));
+    q.kstart = q.kstop = 0;
+    return q;
+#else
+    return *p;
+#endif
+}
 
 // exact carrier phase (cycles, incl. troposphere) of one pixel at one pulse, FP64
 __device__ __forceinline__ double exact_cycles(const PixelRec& q, double xx, double t0cyc,
@@ -643,13 +664,48 @@ __device__ __noinline__
 #else
 __device__ __forceinline__
 #endif
-void tile_body_edge(PairState& S, float& jf, unsigned& jjmax, uint32_t lines_addr,
-                    uint32_t row_bytes, int wlo, unsigned jmax, float Gr, unsigned krel0,
-                    unsigned krel1, int zero, uint32_t bank)
+unsigned tile_body_edge(PairState& S, float jf, unsigned jjmax, uint32_t lines_addr,
+                        uint32_t row_bytes, int wlo, unsigned jmax, float Gr, unsigned krel0,
+                        unsigned krel1, int zero, uint32_t bank)
 {
+    // (jf, jjmax by value: only the pair state has to live in memory around the call)
     tile_body<K, D, Coef, true, TK>(S, jf, jjmax, lines_addr, row_bytes, wlo, jmax, Gr, krel0, krel1, zero, bank);
+    return jjmax;
 }
 
+// Tap pair by tap pair: the two weights of a pair are consumed by their four MACs right
+// away, so only 4 weight registers are live at a time instead of 2 K (source order for ptxas:
+// leaves room to hoist the next pulse's window loads).
+#ifndef I3B_PAIRWISE_MAC
+#define I3B_PAIRWISE_MAC 0
+#endif
+template<int K, int D, class Coef, int OFF, int M = 0>
+struct PairwiseMac {
+    typedef Weights<K, D, Coef> WT;
+    template<int NS>
+    __device__ static __forceinline__ void run(f32x2 f, f32x2 h, f32x2 nf, const f32x2 (&sm)[NS],
+                                               f32x2& a0, f32x2& a1, const typename WT::Top& top)
+    {
+        if constexpr (M < K / 2) {
+            f32x2 wl, wh;
+            WT::template pair<M>(f, h, nf, wl, wh, top);
+            float w0, w1;
+            unpack2(wl, w0, w1);
+            a0 = fma2(bcast2(w0), sm[M + OFF], a0);
+            a1 = fma2(bcast2(w1), sm[M + OFF + 1], a1);
+            unpack2(wh, w0, w1);
+            a0 = fma2(bcast2(w0), sm[K - 1 - M + OFF], a0);
+            a1 = fma2(bcast2(w1), sm[K - M + OFF], a1);
+            PairwiseMac<K, D, Coef, OFF, M + 1>::run(f, h, nf, sm, a0, a1, top);
+        } else if constexpr (K & 1) {
+            const f32x2 wc = WT::center(h, top);
+            float w0, w1;
+            unpack2(wc, w0, w1);
+            a0 = fma2(bcast2(w0), sm[K / 2 + OFF], a0);
+            a1 = fma2(bcast2(w1), sm[K / 2 + OFF + 1], a1);
+        }
+    }
+};
 
 // ---- steady sub-tiles --------------------------------------------------------------------
 // Over a handful of pulses the sample coordinate of a pixel moves by a small fraction of a
@@ -670,6 +726,21 @@ void tile_body_edge(PairState& S, float& jf, unsigned& jjmax, uint32_t lines_add
 #ifndef I3B_SUB
 #define I3B_SUB 8
 #endif
+#ifndef I3B_STEADY_MAX_TAPS
+#define I3B_STEADY_MAX_TAPS 32
+#endif
+// Inside a steady run the phase is the QUADRATIC through the cubic's values at the first,
+// middle and last pulse of the run (one FFMA2 less per pulse); the cubic term it drops is
+// |c3| * 0.048 (SUB-1)^3 rad at most -- ~1e-8 rad for orbital and airborne geometries -- and
+// segments where that bound exceeds 2e-6 rad take the per-pulse path with the full cubic.
+#ifndef I3B_QUAD_RUN
+#define I3B_QUAD_RUN 1
+#endif
+// The first run of a staged tile also tests the whole tile (TK pulses); when that holds the
+// following runs of the tile skip their own test.
+#ifndef I3B_HIER_CHECK
+#define I3B_HIER_CHECK 0 // (measured: -2 % at K = 9, the carried state costs more than the test)
+#endif
 constexpr int SUB = I3B_SUB; // pulses per steady run
 static_assert(TK % SUB == 0, "a staged pulse tile is a whole number of steady runs");
 
@@ -681,13 +752,21 @@ __device__ __forceinline__ void subtile_steady(PairState& S, f32x2 A0, f32x2 A1,
     typedef Weights<K, D, Coef> WT;
     typename WT::Top top;
     WT::load_top(top, zero, bank);
-#pragma unroll
+    // narrow kernels: fully unrolled (pulse offsets are immediates); wide ones (hundreds of
+    // instructions per pulse already) keep a rolled loop with a running offset
+    constexpr int kUnroll = (K >= 16) ? 1 : NP;
+    float xf = 0.f;
+#pragma unroll kUnroll
     for (int x = 0; x < NP; ++x) {
         // carrier phase of both pixels x pulses into the run (cubic re-centred on the run)
         f32x2 ang = A0;
-        if (x > 0) {
+        if constexpr (K >= 16) {
+            const f32x2 X = bcast2(xf);
+            ang = I3B_QUAD_RUN ? fma2(fma2(A2, X, A1), X, A0) : fma2(fma2(fma2(A3, X, A2), X, A1), X, A0);
+            xf += 1.0f;
+        } else if (x > 0) {
             const f32x2 X = bcast2((float) x);
-            ang = fma2(fma2(fma2(A3, X, A2), X, A1), X, A0);
+            ang = I3B_QUAD_RUN ? fma2(fma2(A2, X, A1), X, A0) : fma2(fma2(fma2(A3, X, A2), X, A1), X, A0);
         }
         const f32x2 f = fma2(ang, bcast2(Gr), fbase); // centred fraction (integer part is fixed)
         float ang0, ang1, cs0, sn0, cs1, sn1;
@@ -708,9 +787,16 @@ __device__ __forceinline__ void subtile_steady(PairState& S, f32x2 A0, f32x2 A1,
                 sm[2 * i] = pack2(v4.x, v4.y);
                 sm[2 * i + 1] = pack2(v4.z, v4.w);
             }
+#if I3B_PAIRWISE_MAC
+            const f32x2 h = mul2(f, f), nf = mul2(f, bcast2(-1.0f));
+            f32x2 a0 = 0ull, a1 = 0ull;
+            PairwiseMac<K, D, Coef, OFF>::run(f, h, nf, sm, a0, a1, top);
+            rotate_accumulate<false>(S, a0, a1, cs0, sn0, cs1, sn1, true, true);
+#else
             f32x2 w[K];
             WT::eval(f, w, top);
             mac_rotate<K, OFF, false>(S, w, sm, cs0, sn0, cs1, sn1, true, true);
+#endif
         }
         src += row_bytes;
     }
@@ -906,7 +992,7 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, const __grid_
         const int b0 = t0 & ~(SEG - 1);
 #pragma unroll
         for (int p = 0; p < PX; ++p) {
-            const PixelRec q = pix[gidx[p]];
+            const PixelRec q = load_pixel(pix + gidx[p]);
             const double xx = q.x * q.x + q.y * q.y + q.z * q.z, tc = P.fc * q.tau_atm;
             ybnd[4 * p + 1] = exact_cycles(q, xx, tc, pulse[b0 - SEG]);
             ybnd[4 * p + 2] = exact_cycles(q, xx, tc, pulse[b0]);
@@ -936,7 +1022,7 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, const __grid_
             float c1[PX], c2[PX], c3[PX], a0[PX], f0[PX];
 #pragma unroll
             for (int p = 0; p < PX; ++p) {
-                const PixelRec q = pix[gidx[p]];
+                const PixelRec q = load_pixel(pix + gidx[p]);
                 const double xx = q.x * q.x + q.y * q.y + q.z * q.z, tc = P.fc * q.tau_atm;
                 const double y0 = ybnd[4 * p + 1], y1 = ybnd[4 * p + 2], y2 = ybnd[4 * p + 3];
                 const double y3 = exact_cycles(q, xx, tc, pulse[b + 2 * SEG]);
@@ -965,7 +1051,13 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, const __grid_
             // steady run: |u''| (SUB-1)^2 / 8, u'' = Gr (2 c2 + 6 c3 j), j < SEG
             const float curv0 = 2.f * fabsf(c2[0]) + (6.f * SEG) * fabsf(c3[0]);
             const float curv1 = 2.f * fabsf(c2[1]) + (6.f * SEG) * fabsf(c3[1]);
-            S.flim = 0.5f - 1e-5f - fabsf(Gr) * fmaxf(curv0, curv1) * ((SUB - 1) * (SUB - 1) / 8.0f);
+            // (curvature over a whole tile: the hierarchical test looks TK pulses ahead)
+            constexpr int kHorizon = I3B_HIER_CHECK ? TK : SUB;
+            S.flim = 0.5f - 1e-5f - fabsf(Gr) * fmaxf(curv0, curv1) * ((kHorizon - 1) * (kHorizon - 1) / 8.0f);
+            if (I3B_QUAD_RUN) {
+                constexpr float kDev = 0.0481125f * (SUB - 1) * (SUB - 1) * (SUB - 1);
+                if (fmaxf(fabsf(c3[0]), fabsf(c3[1])) * kDev > 2e-6f) S.flim = -1.0f;
+            }
         }
 
         const int s = n % NSTAGE;
@@ -973,8 +1065,12 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, const __grid_
         const uint32_t lines_addr = stage_addr0 + (uint32_t) s * (uint32_t) sbytes;
         const int wlo = hdr->winlo[s];
         if (I3B_EDGE_SPLIT && kt >= ks_max && kt + TK <= ke_min) {
-#if I3B_STEADY
+            // (32 taps: the rolled steady loop gains nothing over the per-pulse path, measured)
+            if constexpr (I3B_STEADY && K < I3B_STEADY_MAX_TAPS) {
             const int iw0 = S.i0rel[0] - wlo, iw1 = S.i0rel[1] - wlo;
+            bool tile_steady = false; // proven for the whole tile by the first run's test
+            f32x2 tt = 0ull;
+            unsigned jj0 = 0;
 #pragma unroll 1
             for (int sub = 0; sub < TK / SUB; ++sub) {
                 const float js = (float) (kt - seg_b + sub * SUB);
@@ -982,28 +1078,46 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, const __grid_
                 // phase cubic re-centred on the run: ang(js + x) = A0 + A1 x + A2 x^2 + A3 x^3
                 const f32x2 js2 = bcast2(js), Gr2 = bcast2(Gr);
                 const f32x2 c3x3 = mul2(S.c3, bcast2(3.0f)), c2x2 = add2(S.c2, S.c2);
-                const f32x2 A2 = fma2(c3x3, js2, S.c2);
-                const f32x2 A1 = fma2(fma2(c3x3, js2, c2x2), js2, S.c1);
+                f32x2 A2 = fma2(c3x3, js2, S.c2);
+                f32x2 A1 = fma2(fma2(c3x3, js2, c2x2), js2, S.c1);
                 const f32x2 A0 = fma2(fma2(fma2(S.c3, js2, S.c2), js2, S.c1), js2, S.ang0);
-                const f32x2 XE = bcast2((float) (SUB - 1));
-                const f32x2 ange = fma2(fma2(fma2(S.c3, XE, A2), XE, A1), XE, A0);
-                // coordinate (minus floor(base) + 1/2) at both ends of the run
-                const f32x2 g0 = fma2(A0, Gr2, S.f0m), ge = fma2(ange, Gr2, S.f0m);
-                const f32x2 mm = add2(g0, bcast2(MAGIC32));
-                const f32x2 tt = add2(mm, bcast2(-MAGIC32)); // integer part at the first pulse
-                const f32x2 fa = sub2(g0, tt), fe = sub2(ge, tt);
-                float m0, m1, fa0, fa1, fe0, fe1;
-                unpack2(mm, m0, m1);
-                unpack2(fa, fa0, fa1);
-                unpack2(fe, fe0, fe1);
-                const unsigned jj0 = (unsigned) (iw0 + __float_as_int(m0));
-                const unsigned jj1 = (unsigned) (iw1 + __float_as_int(m1));
-                const float worst = fmaxf(fmaxf(fabsf(fa0), fabsf(fa1)), fmaxf(fabsf(fe0), fabsf(fe1)));
-                // steady: same integer part over the whole run (both pixels), adjacent windows
-                // inside the staged rows
-                if (worst <= S.flim && jj1 == jj0 + 1u && jj0 < jmax) {
+                bool steady = tile_steady;
+                if (!(I3B_HIER_CHECK && tile_steady)) {
+                    // coordinate (minus floor(base) + 1/2) at the first pulse and at the last pulse
+                    // of the run (and, for the first run, of the tile)
+                    const f32x2 XE = bcast2((float) (SUB - 1));
+                    const f32x2 ange = fma2(fma2(fma2(S.c3, XE, A2), XE, A1), XE, A0);
+                    const f32x2 g0 = fma2(A0, Gr2, S.f0m), ge = fma2(ange, Gr2, S.f0m);
+                    const f32x2 mm = add2(g0, bcast2(MAGIC32));
+                    tt = add2(mm, bcast2(-MAGIC32)); // integer part at the first pulse
+                    const f32x2 fa = sub2(g0, tt), fe = sub2(ge, tt);
+                    float m0, m1, fa0, fa1, fe0, fe1;
+                    unpack2(mm, m0, m1);
+                    unpack2(fa, fa0, fa1);
+                    unpack2(fe, fe0, fe1);
+                    jj0 = (unsigned) (iw0 + __float_as_int(m0));
+                    const unsigned jj1 = (unsigned) (iw1 + __float_as_int(m1));
+                    const float worst = fmaxf(fmaxf(fabsf(fa0), fabsf(fa1)), fmaxf(fabsf(fe0), fabsf(fe1)));
+                    // steady: same integer part over the whole run (both pixels), adjacent windows
+                    // inside the staged rows
+                    steady = worst <= S.flim && jj1 == jj0 + 1u && jj0 < jmax;
+                    if (I3B_HIER_CHECK && sub == 0 && steady) {
+                        const f32x2 XT = bcast2((float) (TK - 1));
+                        const f32x2 angt = fma2(fma2(fma2(S.c3, XT, A2), XT, A1), XT, A0);
+                        const f32x2 ft = sub2(fma2(angt, Gr2, S.f0m), tt);
+                        float ft0, ft1;
+                        unpack2(ft, ft0, ft1);
+                        tile_steady = fmaxf(fabsf(ft0), fabsf(ft1)) <= S.flim;
+                    }
+                }
+                if (steady) {
                     const uint32_t src = la + ((jj0 >> 1) << 4);
                     const f32x2 fbase = sub2(S.f0m, tt);
+                    if (I3B_QUAD_RUN) {
+                        // quadratic through the cubic at x = 0, (SUB-1)/2, SUB-1
+                        A1 = fma2(S.c3, bcast2(-0.5f * (SUB - 1) * (SUB - 1)), A1);
+                        A2 = fma2(S.c3, bcast2(1.5f * (SUB - 1)), A2);
+                    }
                     if (jj0 & 1u)
                         subtile_steady<K, D, Coef, 1, SUB>(S, A0, A1, A2, S.c3, fbase, Gr, src, row_bytes, P.zero, poly_addr);
                     else
@@ -1013,10 +1127,10 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, const __grid_
                     tile_body<K, D, Coef, false, SUB>(S, jf, jjmax, la, row_bytes, wlo, jmax, Gr, 0u, 0u, P.zero, poly_addr);
                 }
             }
-#else
+            } else {
             jf = (float) (kt - seg_b);
             tile_body<K, D, Coef, false, TK>(S, jf, jjmax, lines_addr, row_bytes, wlo, jmax, Gr, 0u, 0u, P.zero, poly_addr);
-#endif
+            }
         } else {
             // k - kstart for the first pulse of the tile, per pixel
             const unsigned krel0 = (unsigned) (kt - S.kstart[0]);
@@ -1025,7 +1139,7 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, const __grid_
             // (through a copy: the out-of-line call wants its argument in memory, and the
             // interior paths should not find their pair state there)
             PairState T = S;
-            tile_body_edge<K, D, Coef>(T, jf, jjmax, lines_addr, row_bytes, wlo, jmax, Gr, krel0, krel1, P.zero, poly_addr);
+            jjmax = tile_body_edge<K, D, Coef>(T, jf, jjmax, lines_addr, row_bytes, wlo, jmax, Gr, krel0, krel1, P.zero, poly_addr);
             S.accp[0] = T.accp[0]; S.accp[1] = T.accp[1];
             S.accq[0] = T.accq[0]; S.accq[1] = T.accq[1];
         }
@@ -1058,6 +1172,7 @@ struct FitResult {
     bool ok;
     int K, D;
     double max_err;
+    int pair_deg[MAX_TAPS / 2 + 1]; // degree of each tap pair's polynomial (<= D)
     float even[MAX_TAPS / 2 + 1][MAX_COEF / 2];
     float odd[MAX_TAPS / 2 + 1][MAX_COEF / 2];
     TapPoly rows[MAX_TAPS / 2 + 1];
@@ -1094,6 +1209,54 @@ static void fit_tap(const DevKernel& k, double cm, int D, double* mono /*[D+1] i
     }
 }
 
+// One tap pair (taps m and K-1-m, mirror images of each other) at degree D: symmetrised
+// monomial coefficients as floats and the residual of the float Horner evaluation against the
+// caller's kernel.
+static double fit_pair(const DevKernel& k, int K, int m, int D, float* even, float* odd)
+{
+    const double cm = m - 0.5 * (K - 1);
+    double mono[MAX_COEF + 1] = {};
+    fit_tap(k, cm, D, mono);
+    // taps m and K-1-m are mirror images: symmetrise (w_m(f) = E + f O, w_{K-1-m} = E - f O)
+    if (2 * m != K - 1) {
+        double mono2[MAX_COEF + 1] = {};
+        fit_tap(k, -cm, D, mono2);
+        for (int p = 0; p <= D; ++p) {
+            const double mir = (p & 1) ? -mono2[p] : mono2[p];
+            mono[p] = 0.5 * (mono[p] + mir);
+        }
+    } else {
+        for (int p = 1; p <= D; p += 2) mono[p] = 0.0;
+    }
+    for (int i = 0; i < MAX_COEF / 2; ++i) even[i] = odd[i] = 0.f;
+    for (int p = 0; p <= D; ++p) {
+        if (p & 1) odd[p / 2] = (float) mono[p];
+        else even[p / 2] = (float) mono[p];
+    }
+    const int NE = D / 2 + 1, NO = (D + 1) / 2;
+    double worst = 0;
+    for (int j = 0; j <= 400; ++j) {
+        const float f = (float) (-0.5 + j / 400.0);
+        const float h = f * f;
+        float e = even[NE - 1];
+        for (int i = NE - 2; i >= 0; --i) e = fmaf(e, h, even[i]);
+        float o = odd[NO - 1];
+        for (int i = NO - 2; i >= 0; --i) o = fmaf(o, h, odd[i]);
+        const double wp = fmaf(f, o, e), wm = fmaf(-f, o, e);
+        worst = std::max(worst, std::fabs(wp - (double) kernel_eval(k, cm - (double) f)));
+        if (2 * m != K - 1)
+            worst = std::max(worst, std::fabs(wm - (double) kernel_eval(k, -cm - (double) f)));
+    }
+    return worst;
+}
+
+// Outer tap pairs carry small weights and are fitted by low degrees to the same absolute
+// accuracy; every pair gets the LOWEST degree whose residual is within PAIR_TOL, or within 1.5x
+// of what the maximum degree achieves for it (pairs limited by the table's own interpolation
+// error gain nothing from more terms).
+constexpr double PAIR_TOL = 8e-6;
+constexpr int MIN_DEGREE = 2;
+
 static FitResult fit_kernel(const DevKernel& k, double tol)
 {
     FitResult R;
@@ -1104,38 +1267,22 @@ static FitResult fit_kernel(const DevKernel& k, double tol)
     const int nh = (K + 1) / 2;
     double worst = 0;
     for (int m = 0; m < nh; ++m) {
-        const double cm = m - 0.5 * (K - 1);
-        double mono[MAX_COEF + 1] = {};
-        fit_tap(k, cm, D, mono);
-        // taps m and K-1-m are mirror images: symmetrise (w_m(f) = E + f O, w_{K-1-m} = E - f O)
-        double mono2[MAX_COEF + 1] = {};
-        if (2 * m != K - 1) {
-            fit_tap(k, -cm, D, mono2);
-            for (int p = 0; p <= D; ++p) {
-                const double mir = (p & 1) ? -mono2[p] : mono2[p];
-                mono[p] = 0.5 * (mono[p] + mir);
+        float ev[MAX_COEF / 2], od[MAX_COEF / 2];
+        const double r_full = fit_pair(k, K, m, D, R.even[m], R.odd[m]);
+        double r_used = r_full;
+        int d_used = D;
+        for (int d = MIN_DEGREE; d < D; ++d) {
+            const double r = fit_pair(k, K, m, d, ev, od);
+            if (r <= std::max(PAIR_TOL, 1.5 * r_full)) {
+                std::memcpy(R.even[m], ev, sizeof ev);
+                std::memcpy(R.odd[m], od, sizeof od);
+                r_used = r;
+                d_used = d;
+                break;
             }
-        } else {
-            for (int p = 1; p <= D; p += 2) mono[p] = 0.0;
         }
-        for (int p = 0; p <= D; ++p) {
-            if (p & 1) R.odd[m][p / 2] = (float) mono[p];
-            else R.even[m][p / 2] = (float) mono[p];
-        }
-        // residual of the float Horner evaluation against the caller's kernel
-        for (int j = 0; j <= 400; ++j) {
-            const float f = (float) (-0.5 + j / 400.0);
-            const float h = f * f;
-            const int NE = D / 2 + 1, NO = (D + 1) / 2;
-            float e = R.even[m][NE - 1];
-            for (int i = NE - 2; i >= 0; --i) e = fmaf(e, h, R.even[m][i]);
-            float o = R.odd[m][NO - 1];
-            for (int i = NO - 2; i >= 0; --i) o = fmaf(o, h, R.odd[m][i]);
-            const double wp = fmaf(f, o, e), wm = fmaf(-f, o, e);
-            worst = std::max(worst, std::fabs(wp - (double) kernel_eval(k, cm - (double) f)));
-            if (2 * m != K - 1)
-                worst = std::max(worst, std::fabs(wm - (double) kernel_eval(k, -cm - (double) f)));
-        }
+        R.pair_deg[m] = d_used;
+        worst = std::max(worst, r_used);
     }
     for (int m = 0; m < nh; ++m)
         for (int i = 0; i < MAX_COEF / 2; ++i) {
@@ -1161,6 +1308,9 @@ static int match_imm_table(const FitResult& R)
     for (int v = 0; v < imm::kNumTables; ++v) {
         const imm::Desc& d = imm::kDesc[v];
         if (d.taps != R.K || d.degree != R.D) continue;
+        bool same_degrees = true;
+        for (int m = 0; m < (R.K + 1) / 2; ++m) same_degrees = same_degrees && d.pair_deg[m] == R.pair_deg[m];
+        if (!same_degrees) continue;
         double worst = 0;
         for (int m = 0; m < (R.K + 1) / 2; ++m)
             for (int i = 0; i < MAX_COEF / 2; ++i) {
@@ -1196,11 +1346,13 @@ int fast_fit(const DevKernel& hk, I3B_TapPolyFit* fit, char* why, size_t why_len
     const FitResult R = fit_kernel(hk, FIT_TOL);
     fit->degree = R.D;
     fit->max_err = R.max_err;
-    for (int m = 0; m < (R.K + 1) / 2; ++m)
+    for (int m = 0; m < (R.K + 1) / 2; ++m) {
+        fit->pair_degree[m] = R.pair_deg[m];
         for (int i = 0; i < MAX_COEF / 2; ++i) {
             fit->even[m][i] = R.even[m][i];
             fit->odd[m][i] = R.odd[m][i];
         }
+    }
     fit->imm_variant = imm_enabled() ? match_imm_table(R) : -1;
     if (!taps_supported(hk.taps)) {
         snprintf(why, why_len, "tap count %d has no fast instantiation (3..13, 16, 32)", hk.taps);

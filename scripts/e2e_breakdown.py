@@ -4,7 +4,7 @@ from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import numpy as np
 import torch
-from isce3_b200 import synth
+from testkit import synth
 from isce3_b200.focus import backproject, last_stats
 
 scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0

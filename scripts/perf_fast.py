@@ -3,7 +3,7 @@ import sys, time
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import numpy as np
-from isce3_b200 import synth
+from testkit import synth
 from isce3_b200.focus import BackprojectPlan
 
 scale = float(sys.argv[1]) if len(sys.argv) > 1 else 0.5

@@ -3,7 +3,7 @@ import sys, time
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import numpy as np
-from isce3_b200 import synth
+from testkit import synth
 from isce3_b200.focus import backproject, last_stats
 from oracle import tdbp
 

@@ -20,7 +20,8 @@ from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import numpy as np
 
-from isce3_b200 import core, point_target, synth
+from isce3_b200 import core
+from testkit import synth, irf as point_target
 from isce3_b200.focus import backproject, last_stats
 from oracle import tdbp
 

@@ -25,11 +25,11 @@ import math
 
 import numpy as np
 
-from . import core
-from .container import RadarGeometry
-from .core import DateTime, LookSide, LUT2d, Orbit, speed_of_light as C0
-from .geometry import DEMInterpolator
-from .product import RadarGridParameters
+from isce3_b200 import core
+from isce3_b200.container import RadarGeometry
+from isce3_b200.core import DateTime, LookSide, LUT2d, Orbit, speed_of_light as C0
+from isce3_b200.geometry import DEMInterpolator
+from isce3_b200.product import RadarGridParameters
 
 A_WGS84 = core.earth_semi_major_axis
 E2_WGS84 = core.earth_eccentricity_squared
@@ -273,7 +273,7 @@ def synthetic_dem_projected(epsg, lon_c, lat_c, half_extent_m, posting_m=30.0, h
                             method="biquintic"):
     """Same kind of smooth relief on a grid of projected coordinates (UTM / polar
     stereographic / EASE-2), north-up, centred on (lon_c, lat_c) [radians]."""
-    from .projections import make_projection
+    from isce3_b200.projections import make_projection
     xc, yc = make_projection(epsg).forward(lon_c, lat_c)
     n = int(round(2 * half_extent_m / posting_m)) + 1
     x = xc - half_extent_m + np.arange(n) * posting_m
@@ -301,7 +301,7 @@ def _dem_sample_fn(dem: DEMInterpolator):
     if not dem.have_raster:
         return lambda lon, lat: dem.ref_height
 
-    from .projections import make_projection
+    from isce3_b200.projections import make_projection
     proj = make_projection(dem.epsg_code)
 
     def f(lon, lat):
@@ -403,7 +403,7 @@ def make_scene(name="c1", *, pulses=None, bins=None, out_lines=None, out_samples
         if dem_epsg in (None, 4326):
             dem = synthetic_dem(math.degrees(ctr[0]), math.degrees(ctr[1]), min(half_deg, 3.0))
         else:
-            from .projections import utm_epsg_for
+            from isce3_b200.projections import utm_epsg_for
             code = utm_epsg_for(ctr[0], ctr[1]) if dem_epsg == "utm" else int(dem_epsg)
             dem = synthetic_dem_projected(code, ctr[0], ctr[1], min(swath_m, 3.0e5))
     else:

@@ -13,7 +13,8 @@ import math
 import numpy as np
 import pytest
 
-from isce3_b200 import _capi, core, synth
+from isce3_b200 import _capi, core
+from testkit import synth
 
 C0 = 299792458.0
 SEG, TK = 64, 16

@@ -12,7 +12,8 @@ import math
 import numpy as np
 import pytest
 
-from isce3_b200 import core, focus, point_target, synth
+from isce3_b200 import core, focus
+from testkit import synth, irf as point_target
 from isce3_b200.container import RadarGeometry
 from isce3_b200.core import LookSide, LUT2d, OrbitInterpMethod
 from isce3_b200.focus import BackprojectPlan, backproject, last_stats
@@ -289,7 +290,7 @@ def test_one_launch_per_slab_equals_one_launch(oracle):
     import sys
     code = """
 import numpy as np, sys
-from isce3_b200 import synth
+from testkit import synth
 from isce3_b200.focus import backproject, last_stats
 sc = synth.make_scene("c2", pulses=3072, bins=1024, out_lines=37, out_samples=203, n_targets=1)
 shape = (37, 203)

@@ -6,7 +6,8 @@ import math
 import numpy as np
 import pytest
 
-from isce3_b200 import core, synth
+from isce3_b200 import core
+from testkit import synth
 from isce3_b200.core import LookSide, LUT2d, Orbit, OrbitInterpMethod
 from isce3_b200.geometry import DEMInterpolator
 
@@ -353,7 +354,7 @@ def test_projected_dem_sampling_matches_between_oracles(oracles):
     """DEMInterpolator.interpolateLonLat on a UTM raster: port (restated projection + sampler)
     vs reference projection + sampler."""
     import math
-    from isce3_b200 import synth
+    from testkit import synth
     from isce3_b200.projections import utm_epsg_for
     lon, lat = math.radians(-118.3), math.radians(34.1)
     dem = synth.synthetic_dem_projected(utm_epsg_for(lon, lat), lon, lat, 20e3, posting_m=100.0)

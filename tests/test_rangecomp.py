@@ -145,7 +145,7 @@ def test_gpu_range_compressed_swath_stays_in_hbm_for_backprojection(oracle):
     so that compressing them gives the chirp's autocorrelation around each target) are
     compressed on the GPU into HBM and focused from there; the result equals focusing the
     host copy of the same compressed data, and matches the CPU reference on it."""
-    from isce3_b200 import synth
+    from testkit import synth
     from isce3_b200.focus import RangeComp, backproject, last_stats
     sc = synth.make_scene("c2", pulses=2048, bins=1024, out_lines=16, out_samples=200, n_targets=1, noise_db=False)
     chirp = orc.form_linear_chirp(20e6 / 20e-6, 20e-6, 24e6)           # 481 samples

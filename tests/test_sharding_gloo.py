@@ -22,7 +22,7 @@ def _worker(rank, world, store_path, result_path):
     sys.path.insert(0, str(ROOT))
     os.environ["OMP_NUM_THREADS"] = "2"
     import bench
-    from isce3_b200 import synth
+    from testkit import synth
     from oracle import tdbp
     dist.init_process_group("gloo", init_method=f"file://{store_path}", rank=rank, world_size=world)
     sc = synth.make_scene("c2", pulses=512, bins=512, out_lines=11, out_samples=24, n_targets=1)
@@ -51,7 +51,7 @@ def _worker(rank, world, store_path, result_path):
 def test_azimuth_block_sharding_world_size_2(oracles):
     port, _ = oracles
     import bench
-    from isce3_b200 import synth
+    from testkit import synth
     # block bounds tile the line range exactly, for ragged splits too
     for lines in (11, 8, 3, 1):
         for world in (1, 2, 4, 8):
