@@ -1,23 +1,36 @@
-"""Developer tool: timing breakdown of the one-shot (host-buffer) call on the C2 frame."""
+"""Developer tool: timing breakdown of the one-shot (host-buffer) call.
+Usage: e2e_breakdown.py [config=c2] [pinned|pageable|both] [iterations]"""
 import sys, time
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import numpy as np
-import torch
 from testkit import synth
-from isce3_b200.focus import backproject, last_stats
+from isce3_b200.focus import BackprojectPlan, backproject, last_stats
 
-scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
-sc = synth.make_scene("c2", pulses=16384, bins=int(12288 * scale), out_lines=int(8192 * scale),
-                      out_samples=int(8192 * scale), noise_db=False, n_targets=1)
+cfg = sys.argv[1] if len(sys.argv) > 1 else "c2"
+mode = sys.argv[2] if len(sys.argv) > 2 else "both"
+iters = int(sys.argv[3]) if len(sys.argv) > 3 else 4
+kw = {"n_targets": 9} if cfg == "c4" else {}
+sc = synth.make_scene(cfg, **kw)
 shape = (sc.out_geometry.grid_length, sc.out_geometry.grid_width)
-pin = torch.empty(sc.rc.shape, dtype=torch.complex64, pin_memory=True).numpy()
-pin[...] = sc.rc
-out = torch.empty(shape, dtype=torch.complex64, pin_memory=True).numpy()
 args = list(sc.backproject_args())
-for host, name in ((pin, "pinned"), (sc.rc, "pageable")):
+with BackprojectPlan(*args) as plan:
+    for _ in range(3):
+        plan.execute()
+    st = plan.stats()
+    print(f"resident: total {st['ms_total']:.1f} solve {st['ms_target_solve']:.1f} accumulate {st['ms_accumulate']:.1f}", flush=True)
+hosts = []
+if mode in ("pinned", "both"):
+    import torch
+    pin = torch.empty(sc.rc.shape, dtype=torch.complex64, pin_memory=True).numpy()
+    pin[...] = sc.rc
+    out = torch.empty(shape, dtype=torch.complex64, pin_memory=True).numpy()
+    hosts.append((pin, out, "pinned"))
+if mode in ("pageable", "both"):
+    hosts.append((sc.rc, np.empty(shape, np.complex64), "pageable"))
+for host, out, name in hosts:
     args[1] = host
-    for it in range(5):
+    for it in range(iters):
         t = time.perf_counter()
         backproject(out, *args)
         dt = (time.perf_counter() - t) * 1e3

@@ -95,6 +95,33 @@ def test_specialised_and_general_fast_kernels_agree(oracle, monkeypatch):
     check(bank, cpu, sc)
 
 
+def test_irf_metrics_match_oracle_nov128_chip64(oracle):
+    """The IRF gate exactly as SURVEY.md 8d / the reference test specify it
+    (tests/python/extensions/pybind/focus/backproject.py:141-170): nov = 128 on a 64-pixel
+    chip; peak location within 0.01 sample, PSLR and ISLR within 0.05 dB, both axes."""
+    sc = synth.make_scene("c2", pulses=5120, bins=1024, out_lines=72, out_samples=72, n_targets=1,
+                          noise_db=False)
+    _, og, _, st = run_gpu(sc)
+    _, oc, _ = run_cpu(oracle, sc)
+    assert st["used_fast_kernel"] == 1
+    r = np.asarray(sc.out_geometry.slant_range)
+    carrier = np.exp(-1j * 4 * np.pi / (core.speed_of_light / sc.fc) * r)[None, :]
+    tg = sc.targets[0]
+    ig, _ = point_target.analyze_point_target(og * carrier, tg.az_index, tg.rg_index, nov=128, chipsize=64)
+    ic, _ = point_target.analyze_point_target(oc * carrier, tg.az_index, tg.rg_index, nov=128, chipsize=64)
+    for axis in ("azimuth", "range"):
+        assert abs(ig[axis]["offset"] - ic[axis]["offset"]) <= 0.01
+        assert abs(ig[axis]["PSLR"] - ic[axis]["PSLR"]) <= 0.05
+        assert abs(ig[axis]["ISLR"] - ic[axis]["ISLR"]) <= 0.05
+        assert abs(ic[axis]["offset"]) < 0.05
+    assert abs(ig["phase"] - ic["phase"]) <= PHASE_TOL
+    # the reference test's own thresholds: position within resolution / 128, range width <= c / 2B
+    dr = sc.out_geometry.radar_grid.range_pixel_spacing
+    assert dr * ig["range"]["resolution"] <= core.speed_of_light / (2 * sc.range_bandwidth)
+    for axis in ("azimuth", "range"):
+        assert abs(ig[axis]["offset"]) <= ig[axis]["resolution"] / 128 + 0.01
+
+
 def test_irf_metrics_match_oracle(oracle):
     """Point-target IRF of the GPU image vs the oracle image: peak location within 0.01
     sample, PSLR and ISLR within 0.05 dB, in both axes (nov = 32 on a 32-pixel chip)."""
@@ -147,6 +174,85 @@ def test_raster_dem_doppler_lut_tsx(oracle):
     cpu = run_cpu(oracle, sc)
     assert np.nanmax(cpu[2]) - np.nanmin(cpu[2]) > 1.0  # the height layer really varies
     check(gpu, cpu, sc)
+
+
+def _doppler_lut(geom, method, lo, hi, b_error=False, shape=(7, 9), range_margin=2.0e4, wiggle=25.0):
+    """Smooth 2-D Doppler LUT covering ``geom``'s grid (and the whole orbit in time)."""
+    g, orbit = geom.radar_grid, geom.orbit
+    y = np.linspace(orbit.start_time, orbit.end_time, shape[0])
+    x = np.linspace(g.starting_range - range_margin,
+                    g.starting_range + g.width * g.range_pixel_spacing + range_margin, shape[1])
+    yy, xx = np.meshgrid(y, x, indexing="ij")
+    data = lo + (hi - lo) * (xx - x[0]) / (x[-1] - x[0]) + \
+        wiggle * np.sin(2 * np.pi * (yy - y[0]) / (y[-1] - y[0]))
+    return LUT2d(x[0], y[0], x[1] - x[0], y[1] - y[0], data, method, b_error)
+
+
+@pytest.mark.parametrize("method", ["bilinear", "bicubic", "biquintic"])
+def test_output_grid_doppler_lut_with_data(oracle, method):
+    """Squinted OUTPUT grid: the output geometry's Doppler LUT holds data (non-zero sin(squint)
+    in rdr2geo), sampled with each 2-D method; the input geometry has a different, bilinear LUT,
+    so geo2rdr does not simply invert rdr2geo (its root is ~0.3 s from the output line's time)."""
+    sc = synth.make_scene("c2", pulses=3072, bins=1536, out_lines=20, out_samples=200, n_targets=1,
+                          doppler_lut=True)
+    sc.out_geometry = RadarGeometry(sc.out_geometry.radar_grid, sc.out_geometry.orbit,
+                                    _doppler_lut(sc.out_geometry, method, -180.0, 220.0))
+    gpu = run_gpu(sc)
+    cpu = run_cpu(oracle, sc)
+    assert gpu[3]["used_fast_kernel"] == 1
+    check(gpu, cpu)
+    # the squint really moved the targets: compare with the zero-Doppler output grid
+    sc0 = synth.make_scene("c2", pulses=3072, bins=1536, out_lines=20, out_samples=200, n_targets=1,
+                           doppler_lut=True)
+    plain = run_gpu(sc0)
+    assert np.linalg.norm(plain[1] - gpu[1]) > 0.5 * np.linalg.norm(plain[1])
+
+
+def test_biquintic_input_doppler_lut(oracle):
+    sc = synth.make_scene("c2", pulses=2048, bins=1024, out_lines=16, out_samples=160, n_targets=1)
+    sc.in_geometry = RadarGeometry(sc.in_geometry.radar_grid, sc.in_geometry.orbit,
+                                   _doppler_lut(sc.in_geometry, "biquintic", -60.0, 90.0))
+    check(run_gpu(sc), run_cpu(oracle, sc))
+
+
+def test_lut_bounds_error_is_reported_and_lookups_are_clamped(oracle):
+    """LUT2d(bounds_error=True) that does not cover the output swath: the CPU reference raises
+    through its error channel (LUT2d.cpp:143-150), the reference CUDA path silently returns
+    ref_value.  Here: the lookup is clamped exactly like bounds_error=False (same image) and the
+    call reports the soft code OutOfBoundsLookup (returns True)."""
+    sc = synth.make_scene("c2", pulses=2048, bins=1024, out_lines=12, out_samples=160, n_targets=1)
+    g = sc.out_geometry.radar_grid
+    images = {}
+    for b_error in (False, True):
+        lut = _doppler_lut(sc.out_geometry, "bilinear", -40.0, 60.0, b_error=b_error,
+                           range_margin=-0.25 * g.width * g.range_pixel_spacing)
+        assert not lut.contains(g.sensing_start, g.starting_range)
+        sc.out_geometry = RadarGeometry(g, sc.out_geometry.orbit, lut)
+        images[b_error] = run_gpu(sc)
+    assert images[False][0] is False and images[True][0] is True
+    np.testing.assert_array_equal(images[True][1], images[False][1])
+    cpu = run_cpu(oracle, sc)  # (the oracle's LUT shim clamps and does not raise)
+    check((cpu[0],) + images[True][1:], cpu)
+
+
+def test_input_geometry_with_its_own_orbit_and_doppler(oracle):
+    """Input and output geometry do NOT share orbit object, sampling or Doppler model: the
+    input orbit is the same trajectory resampled every 5 s (Legendre), the output one every
+    10 s (Hermite), both LUTs hold different data.  geo2rdr's shortcut ("the output line time
+    is the root") must fail its own test and fall back to the bracketed search."""
+    sc = synth.make_scene("c2", pulses=3072, bins=1536, out_lines=16, out_samples=180, n_targets=1)
+    o = sc.out_geometry.orbit
+    t = np.arange(o.start_time, o.end_time + 1e-9, 5.0)
+    pos, vel = synth.interpolate_orbit_many(o, t)
+    own = core.Orbit.from_arrays(float(t[0]), 5.0, pos, vel, o.reference_epoch)
+    own.interp_method = OrbitInterpMethod.LEGENDRE
+    sc.in_geometry = RadarGeometry(sc.in_geometry.radar_grid, own,
+                                   _doppler_lut(sc.in_geometry, "bilinear", 120.0, 260.0))
+    sc.out_geometry = RadarGeometry(sc.out_geometry.radar_grid, o,
+                                    _doppler_lut(sc.out_geometry, "bilinear", -150.0, -30.0))
+    gpu = run_gpu(sc)
+    check(gpu, run_cpu(oracle, sc))
+    assert gpu[3]["pixel_pulses"] > 0
 
 
 @pytest.mark.parametrize("dem_epsg", ["utm", 3413, 6933])
