@@ -322,6 +322,26 @@ int i3b_release_device_memory(void);
 /* Host-only diagnostic: the polynomial fit the fast kernel would use.      */
 int i3b_fit_tap_polynomials(const I3B_Kernel* kernel, I3B_TapPolyFit* fit);
 
+/* ---- per-point geometry as a batch API ---------------------------
+ * The two bracketing solvers of the path for ARRAYS of points, on the current device: what the
+ * other GPU consumers of the reference (cuda/geometry/gpuTopo.cu:185, gpuGeo2rdr.cu:28,
+ * cuda/geocode/Geocode.cu:87) call per thread through cuda/geometry/gpuGeometry.cu:57-68 and
+ * :166-181.  Same semantics as isce3::geometry::rdr2geo_bracket (geometry/rdr2geo_roots.cpp:14-27)
+ * and geo2rdr_bracket (geometry/geo2rdr_roots.cpp:16-25) per point; points that fail are NaN.
+ * Arrays are host arrays (device arrays on the current device with I3B_FLAG_DEVICE_POINTERS).
+ * `status` (optional) receives the per-point ErrorCode; the call returns the last non-success
+ * ErrorCode of any point (0 if all converged) or a negative I3B_EXC_* code.              */
+int i3b_rdr2geo_bracket_batch(const I3B_Orbit* orbit, const I3B_DEM* dem, double wavelength,
+                              int32_t look_side, const I3B_Rdr2GeoBracketParams* params, int64_t n,
+                              const double* aztime, const double* slant_range,
+                              const double* doppler /* [n] or NULL = zero Doppler */,
+                              double* xyz /* [n][3] ECEF m */, int32_t* status /* [n] or NULL */,
+                              uint32_t flags);
+int i3b_geo2rdr_bracket_batch(const I3B_Orbit* orbit, const I3B_LUT2d* doppler, double wavelength,
+                              int32_t look_side, const I3B_Geo2RdrBracketParams* params, int64_t n,
+                              const double* xyz /* [n][3] ECEF m */, double* aztime, double* slant_range,
+                              int32_t* status /* [n] or NULL */, uint32_t flags);
+
 /* ---- range compression (the step that produces `in`) ---------
  * isce3::focus::RangeComp (cxx/isce3/focus/RangeComp.h:13-116, RangeComp.cpp):
  * frequency-domain convolution of each input line with the time-reversed complex

@@ -245,6 +245,8 @@ EXPORTED_SYMBOLS = (
     "i3b_measure_peaks",
     "i3b_fit_tap_polynomials",
     "i3b_release_device_memory",
+    "i3b_rdr2geo_bracket_batch",
+    "i3b_geo2rdr_bracket_batch",
     "i3b_rangecomp_create",
     "i3b_rangecomp_query",
     "i3b_rangecomp_execute",
@@ -295,6 +297,15 @@ def load_library() -> C.CDLL:
     lib.i3b_fit_tap_polynomials.argtypes = [C.POINTER(Kernel), C.POINTER(TapPolyFit)]
     lib.i3b_fit_tap_polynomials.restype = C.c_int
     lib.i3b_release_device_memory.restype = C.c_int
+    lib.i3b_current_device.restype = C.c_int
+    lib.i3b_rdr2geo_bracket_batch.argtypes = [
+        C.POINTER(Orbit), C.POINTER(DEM), C.c_double, C.c_int32, C.POINTER(Rdr2GeoBracketParams), C.c_int64,
+        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+    lib.i3b_rdr2geo_bracket_batch.restype = C.c_int
+    lib.i3b_geo2rdr_bracket_batch.argtypes = [
+        C.POINTER(Orbit), C.POINTER(LUT2d), C.c_double, C.c_int32, C.POINTER(Geo2RdrBracketParams), C.c_int64,
+        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+    lib.i3b_geo2rdr_bracket_batch.restype = C.c_int
     lib.i3b_rangecomp_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
     lib.i3b_rangecomp_create.restype = C.c_int
     lib.i3b_rangecomp_query.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]

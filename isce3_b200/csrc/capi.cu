@@ -145,6 +145,50 @@ private:
     size_t cached_ = 0;
 };
 
+// Small pinned host blocks (device status words read back while the host keeps working);
+// recycled for the life of the process, like the device buffers.
+class PinnedPool {
+public:
+    void* get(size_t bytes)
+    {
+        {
+            std::lock_guard<std::mutex> lock(mtx_);
+            for (size_t i = 0; i < free_.size(); ++i)
+                if (free_[i].second >= bytes) {
+                    void* p = free_[i].first;
+                    sizes_.push_back(free_[i]);
+                    free_.erase(free_.begin() + i);
+                    return p;
+                }
+        }
+        void* p = nullptr;
+        CK(cudaHostAlloc(&p, std::max<size_t>(bytes, 256), cudaHostAllocPortable));
+        std::lock_guard<std::mutex> lock(mtx_);
+        sizes_.push_back({p, std::max<size_t>(bytes, 256)});
+        return p;
+    }
+    void put(void* p)
+    {
+        std::lock_guard<std::mutex> lock(mtx_);
+        for (size_t i = 0; i < sizes_.size(); ++i)
+            if (sizes_[i].first == p) {
+                free_.push_back(sizes_[i]);
+                sizes_.erase(sizes_.begin() + i);
+                return;
+            }
+    }
+
+private:
+    std::mutex mtx_;
+    std::vector<std::pair<void*, size_t>> free_, sizes_;
+};
+
+static PinnedPool& pinned_pool()
+{
+    static PinnedPool* pool = new PinnedPool();
+    return *pool;
+}
+
 static DeviceCache& device_cache()
 {
     static DeviceCache* cache = new DeviceCache(); // leaked on purpose: no CUDA calls at exit
@@ -329,9 +373,14 @@ struct Shard {
     I3B_Stats stats;
     int status_code = 0;
     std::string error;
+    // target solve in flight: its status lands in pinned host memory, `ev_status` fires then
+    DevStatus* status_host = nullptr;
+    std::unique_ptr<Event> ev_solve0, ev_solve1, ev_status;
+    bool solve_pending = false;
 
     ~Shard()
     {
+        if (status_host) pinned_pool().put(status_host);
         // Buffers go back to the cache right after this body, on this thread: make sure
         // nothing is still running on them (error paths may leave work in flight).
         int cur = -1;
@@ -452,27 +501,47 @@ static void shard_setup(const HostScene& hs, Shard& sh)
     sh.stats.taps = A.kernel.taps;
 }
 
-// pulse table + per-pixel target solve; returns the soft/hard status
-static void shard_solve(const HostScene& hs, Shard& sh)
+// pulse table + per-pixel target solve, asynchronous: kernels and the read-back of the status
+// words (into pinned memory) are queued on the compute stream; shard_solve_finish() collects.
+static void shard_solve_launch(const HostScene& hs, Shard& sh)
 {
     CK(cudaSetDevice(sh.device));
     cudaStream_t s = sh.compute;
+    if (!sh.status_host) sh.status_host = static_cast<DevStatus*>(pinned_pool().get(sizeof(DevStatus)));
+    if (!sh.ev_solve0) {
+        sh.ev_solve0.reset(new Event());
+        sh.ev_solve1.reset(new Event());
+        sh.ev_status.reset(new Event());
+    }
     DevStatus init;
     std::memset(&init, 0, sizeof init);
     init.kmin = INT_MAX;
     init.kmax = INT_MIN;
     CK(cudaMemcpyAsync(sh.status.p, &init, sizeof init, cudaMemcpyHostToDevice, s));
-    Event e0, e1;
-    e0.record(s);
+    sh.ev_solve0->record(s);
     launch_pulse_table(sh.sp.in_orbit, sh.sp.in_time, hs.a.fc, sh.pulse.p + kPulsePadLo, sh.pv.p, sh.status.p, s);
     CK(cudaGetLastError());
     launch_target_solve(sh.sp, sh.pix.p, sh.height.p, sh.tile_info.p, (int) sh.tile_info.n, sh.status.p, s);
     CK(cudaGetLastError());
-    e1.record(s);
-    DevStatus st;
-    CK(cudaMemcpyAsync(&st, sh.status.p, sizeof st, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    sh.stats.ms_target_solve = elapsed(e0, e1);
+    sh.ev_solve1->record(s);
+    CK(cudaMemcpyAsync(sh.status_host, sh.status.p, sizeof(DevStatus), cudaMemcpyDeviceToHost, s));
+    sh.ev_status->record(s);
+    sh.solve_pending = true;
+}
+
+static bool shard_solve_ready(Shard& sh)
+{
+    return !sh.solve_pending || cudaEventQuery(sh.ev_status->e) == cudaSuccess;
+}
+
+static void shard_solve_finish(Shard& sh)
+{
+    if (!sh.solve_pending) return;
+    CK(cudaSetDevice(sh.device));
+    CK(cudaEventSynchronize(sh.ev_status->e));
+    sh.solve_pending = false;
+    const DevStatus st = *sh.status_host;
+    sh.stats.ms_target_solve = elapsed(*sh.ev_solve0, *sh.ev_solve1);
     sh.stats.total_launches += 3;
     sh.stats.pixel_pulses = (double) st.pixel_pulses;
     if (st.hard_error) throw ApiError(st.hard_error, "orbit interpolation outside of orbit domain");
@@ -483,6 +552,53 @@ static void shard_solve(const HostScene& hs, Shard& sh)
         sh.stats.pulse_first = st.kmin;
         sh.stats.pulse_last = st.kmax;
     }
+}
+
+static void shard_solve(const HostScene& hs, Shard& sh)
+{
+    shard_solve_launch(hs, sh);
+    shard_solve_finish(sh);
+}
+
+// Pulses the shard's block can possibly integrate, from host-side bounds alone (output line
+// times +- half the longest coherent processing interval of Backproject.cpp:176-193, plus the
+// beam-centre shift the Doppler LUTs allow): what the one-shot call starts uploading WHILE the
+// target solve runs.  The solve's exact range is checked against it afterwards.
+static bool conservative_pulse_range(const HostScene& hs, const Shard& sh, int* k0, int* k1)
+{
+    const I3B_BackprojectArgs& a = hs.a;
+    const I3B_RadarGrid &og = a.out_geometry.grid, &ig = a.in_geometry.grid;
+    if (sh.nlines <= 0 || og.width <= 0 || ig.length <= 0) return false;
+    const I3B_Orbit& orb = a.in_geometry.orbit;
+    double pmax = 0, vmin = 1e300;
+    for (int i = 0; i < orb.n; ++i) {
+        const double* p = orb.pos + 3 * (size_t) i;
+        const double* v = orb.vel + 3 * (size_t) i;
+        pmax = std::max(pmax, std::sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]));
+        vmin = std::min(vmin, std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]));
+    }
+    if (!(pmax > 0) || !(vmin > 0) || !std::isfinite(pmax) || !std::isfinite(vmin)) return false;
+    auto fmax = [](const I3B_LUT2d& l) {
+        if (!l.have_data) return std::fabs(l.ref_value);
+        double m = 0;
+        const size_t n = (size_t) l.length * (size_t) l.width;
+        for (size_t i = 0; i < n; ++i) m = std::max(m, std::fabs(l.data[i]));
+        return m;
+    };
+    const double fd = fmax(a.in_geometry.doppler) + fmax(a.out_geometry.doppler);
+    if (!std::isfinite(fd)) return false;
+    const double wvl = kC / a.fc;
+    const double r_max = 1.05 * (og.starting_range + (og.width - 1) * og.range_pixel_spacing);
+    const double cpi = wvl * r_max * (pmax / 6.30e6) / (2.0 * a.ds * vmin);
+    const double shift = 1.2 * fd * wvl * r_max / (2.0 * vmin * vmin);
+    const double t_first = og.sensing_start + sh.line0 / og.prf;
+    const double t_last = og.sensing_start + (sh.line0 + sh.nlines - 1) / og.prf;
+    const double lo = (std::min(t_first, t_last) - 0.5 * cpi - shift - ig.sensing_start) * ig.prf - 64.0;
+    const double hi = (std::max(t_first, t_last) + 0.5 * cpi + shift - ig.sensing_start) * ig.prf + 64.0;
+    if (!std::isfinite(lo) || !std::isfinite(hi)) return false;
+    *k0 = (int) std::max(0.0, std::min(std::floor(lo), (double) ig.length));
+    *k1 = (int) std::max(0.0, std::min(std::ceil(hi), (double) ig.length));
+    return *k1 > *k0;
 }
 
 // accumulate pulses [k0, k1) (must be staged) into acc
@@ -525,92 +641,187 @@ static void shard_accumulate(Shard& sh, int k0, int k1, cudaStream_t s)
 }
 
 // Stage the needed pulses and integrate them, slab by slab: the copy of slab c+1 runs on the
-// copy stream while slab c is integrated on the compute stream.
+// copy stream while slab c is integrated on the compute stream.  In the one-shot call the
+// target solve may still be running when this starts (shard_solve_launch): the upload then
+// begins with a conservative pulse range and the solve's result is collected on the way.
 static void shard_run(const HostScene& hs, Shard& sh, bool resident_only)
 {
     const I3B_BackprojectArgs& a = hs.a;
     CK(cudaSetDevice(sh.device));
     cudaStream_t s = sh.compute;
     const int nr = sh.ap.nr;
-    const int kfirst = sh.stats.pulse_first, klast = sh.stats.pulse_last;
+    const int tk = fast_pulse_tile();
+    const bool devptr = (a.flags & (I3B_FLAG_DEVICE_POINTERS | I3B_FLAG_DEVICE_INPUT)) != 0;
     CK(cudaMemsetAsync(sh.acc.p, 0, sh.acc.n * sizeof(double2), s));
+    static const bool no_early = [] {
+        const char* e = std::getenv("I3B_NO_EARLY_UPLOAD"); // test / tuning knob
+        return e && std::atoi(e) != 0;
+    }();
+    int c0 = 0, c1 = 0;
+    bool early = sh.solve_pending && !resident_only && !sh.rc_resident && !devptr && !no_early &&
+                 sh.ap.npix > 0 && conservative_pulse_range(hs, sh, &c0, &c1);
+    if (!early) shard_solve_finish(sh);
     Event ea0, ea1;
+    bool ea0_recorded = false;
     double ms_h2d = 0.0;
-    if (klast > kfirst && sh.ap.npix > 0) {
-        const bool devptr = (a.flags & (I3B_FLAG_DEVICE_POINTERS | I3B_FLAG_DEVICE_INPUT)) != 0;
-        if (!sh.rc_resident) {
-            if (devptr && (nr % 2 == 0)) {
-                sh.rc_dev = reinterpret_cast<const float2*>(a.in);
-                sh.rc_pitch = nr;
-                sh.rc_k0 = 0;
-                sh.rc_rows = (int) a.in_geometry.grid.length;
-                sh.rc_resident = true;
-            } else {
-                sh.rc_pitch = (nr + 1) & ~1; // 16-byte line pitch (TMA global stride rule)
-                sh.rc_k0 = kfirst;
-                sh.rc_rows = klast - kfirst;
-                sh.rc.alloc((size_t) sh.rc_rows * sh.rc_pitch, s);
-                sh.rc_dev = sh.rc.p;
-                // pool memory is recycled: clear it, so that rows a pulse tile stages ahead of
-                // the landed slab (and the pad column) never hold stale bit patterns
-                CK(cudaMemsetAsync(sh.rc.p, 0, sh.rc.n * sizeof(float2), sh.copy));
-            }
+    auto stage_input = [&](int b0, int b1) {
+        sh.rc_pitch = (nr + 1) & ~1; // 16-byte line pitch (TMA global stride rule)
+        sh.rc_k0 = b0;
+        sh.rc_rows = b1 - b0;
+        sh.rc.alloc((size_t) sh.rc_rows * sh.rc_pitch, s);
+        sh.rc_dev = sh.rc.p;
+        // pool memory is recycled: clear it, so that rows a pulse tile stages ahead of
+        // the landed slab (and the pad column) never hold stale bit patterns
+        CK(cudaMemsetAsync(sh.rc.p, 0, sh.rc.n * sizeof(float2), sh.copy));
+    };
+    if (early || (sh.stats.pulse_last > sh.stats.pulse_first && sh.ap.npix > 0)) {
+        if (!sh.rc_resident && devptr && (nr % 2 == 0)) {
+            sh.rc_dev = reinterpret_cast<const float2*>(a.in);
+            sh.rc_pitch = nr;
+            sh.rc_k0 = 0;
+            sh.rc_rows = (int) a.in_geometry.grid.length;
+            sh.rc_resident = true;
         }
-        ea0.record(s);
         if (sh.rc_resident) {
+            const int kfirst = sh.stats.pulse_first, klast = sh.stats.pulse_last;
+            ea0.record(s);
+            ea0_recorded = true;
             if (!resident_only) shard_accumulate(sh, kfirst, klast, s);
         } else {
             const float2* in = reinterpret_cast<const float2*>(a.in);
             const int slab = std::max(a.batch, 1);
             std::vector<std::unique_ptr<Event>> landed;
+            std::vector<int> slab_end; // landed[i] fires when pulses < slab_end[i] are on the device
             const auto t0 = std::chrono::steady_clock::now();
+            // I3B_LAUNCH_PER_SLAB=1 (test knob): one launch per slab, like the reference
+            static const bool per_slab = [] {
+                const char* e = std::getenv("I3B_LAUNCH_PER_SLAB");
+                return e && std::atoi(e) != 0;
+            }();
+            int kfirst = 0, klast = 0;   // exact range (known once the solve is in)
+            bool solved = !early;
+            if (solved) {
+                kfirst = sh.stats.pulse_first;
+                klast = sh.stats.pulse_last;
+                stage_input(kfirst, klast);
+            } else {
+                stage_input(c0, c1);
+            }
+            int b0 = sh.rc_k0, b1 = sh.rc_k0 + sh.rc_rows;
+            int pending = kfirst;   // first pulse not yet covered by an accumulation launch
+            int uploaded = b0;      // pulses [b0, uploaded) have been queued for upload
+            bool restart = false;
             // Slabs are copied back to back; an accumulation launch is issued for everything
             // copied so far whenever the compute stream has run dry (and for the first and the
             // last slab), so a fast host link gives 2 launches per call and a slow one a few
             // more -- not one per slab, each of which would re-run every tile's prologue.
-            int pending = kfirst; // first pulse not yet covered by an accumulation launch
-            for (int k = kfirst; k < klast; k += slab) {
-                const int rows = std::min(slab, klast - k);
+            bool first_launch = true;
+            while (true) {
+                if (!solved && (uploaded >= b1 || shard_solve_ready(sh))) {
+                    shard_solve_finish(sh); // (blocks only when everything is already queued)
+                    solved = true;
+                    kfirst = sh.stats.pulse_first;
+                    klast = sh.stats.pulse_last;
+                    pending = kfirst;
+                    if (klast > kfirst && (kfirst < b0 || klast > b1)) {
+                        restart = true; // the bound did not hold (exotic geometry): exact range, again
+                        break;
+                    }
+                }
+                const int stop = solved ? std::min(klast, b1) : b1;
+                if (uploaded >= stop) break;
+                const int k = uploaded;
+                const int rows = std::min(slab, stop - k);
                 CK(cudaMemcpy2DAsync(sh.rc.p + (size_t) (k - sh.rc_k0) * sh.rc_pitch,
                                      (size_t) sh.rc_pitch * sizeof(float2), in + (size_t) k * nr,
                                      (size_t) nr * sizeof(float2), (size_t) nr * sizeof(float2), rows,
                                      devptr ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, sh.copy));
                 landed.emplace_back(new Event());
                 landed.back()->record(sh.copy);
+                slab_end.push_back(k + rows);
                 sh.stats.h2d_bytes += (int64_t) rows * nr * (int64_t) sizeof(float2);
-                if (resident_only) continue;
-                const bool first = k == kfirst, last = k + rows >= klast;
-                // I3B_LAUNCH_PER_SLAB=1 (test knob): one launch per slab, like the reference
-                static const bool per_slab = [] {
-                    const char* e = std::getenv("I3B_LAUNCH_PER_SLAB");
-                    return e && std::atoi(e) != 0;
-                }();
-                if (first || last || per_slab || cudaStreamQuery(s) == cudaSuccess) {
+                uploaded = k + rows;
+                if (resident_only || !solved || klast <= kfirst || uploaded <= pending) continue;
+                const bool last = uploaded >= klast;
+                if (first_launch || last || per_slab || cudaStreamQuery(s) == cudaSuccess) {
                     // launches end on absolute multiples of the staged pulse tile (the last one
                     // at klast): the image is then bit-identical for every batch size and
                     // whatever the host link's timing made of the launch boundaries
-                    const int tk = fast_pulse_tile();
-                    const int kend = last ? klast : ((k + rows) / tk) * tk;
+                    const int kend = last ? klast : (uploaded / tk) * tk;
                     if (kend <= pending) continue;
+                    if (!ea0_recorded) {
+                        ea0.record(s);
+                        ea0_recorded = true;
+                    }
                     CK(cudaStreamWaitEvent(s, landed.back()->e, 0));
                     shard_accumulate(sh, pending, kend, s);
                     pending = kend;
+                    first_launch = false;
                 }
+            }
+            if (restart) {
+                CK(cudaStreamSynchronize(sh.copy));
+                landed.clear();
+                slab_end.clear();
+                stage_input(kfirst, klast);
+                for (int k = kfirst; k < klast; k += slab) {
+                    const int rows = std::min(slab, klast - k);
+                    CK(cudaMemcpy2DAsync(sh.rc.p + (size_t) (k - sh.rc_k0) * sh.rc_pitch,
+                                         (size_t) sh.rc_pitch * sizeof(float2), in + (size_t) k * nr,
+                                         (size_t) nr * sizeof(float2), (size_t) nr * sizeof(float2), rows,
+                                         cudaMemcpyHostToDevice, sh.copy));
+                    sh.stats.h2d_bytes += (int64_t) rows * nr * (int64_t) sizeof(float2);
+                }
+                landed.emplace_back(new Event());
+                landed.back()->record(sh.copy);
+                slab_end.push_back(klast);
+                pending = kfirst;
+            }
+            // Whatever has not been launched yet (with pinned host memory every slab is queued
+            // long before the solve is in): integrate what has LANDED by now right away, the
+            // rest when its copies are done -- the kernel starts while the upload continues.
+            while (!resident_only && solved && klast > pending) {
+                if (!ea0_recorded) {
+                    ea0.record(s);
+                    ea0_recorded = true;
+                }
+                int kend = klast;
+                Event* wait_for = landed.empty() ? nullptr : landed.back().get();
+                if (!restart && cudaStreamQuery(s) == cudaSuccess) {
+                    // compute stream is dry: furthest slab that has landed (at least the one
+                    // holding `pending`, which the launch then waits for)
+                    size_t j = 0;
+                    while (j < slab_end.size() && slab_end[j] <= pending) ++j;
+                    size_t best = j;
+                    for (size_t i = j; i < slab_end.size(); ++i) {
+                        if (cudaEventQuery(landed[i]->e) != cudaSuccess) break;
+                        best = i;
+                    }
+                    if (best < slab_end.size() && slab_end[best] < klast) {
+                        const int cut = (slab_end[best] / tk) * tk;
+                        if (cut > pending) {
+                            kend = cut;
+                            wait_for = landed[best].get();
+                        }
+                    }
+                }
+                if (wait_for) CK(cudaStreamWaitEvent(s, wait_for->e, 0));
+                shard_accumulate(sh, pending, kend, s);
+                pending = kend;
             }
             CK(cudaStreamSynchronize(sh.copy));
             ms_h2d = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
             if (resident_only) sh.rc_resident = true;
         }
-        ea1.record(s);
-    } else {
-        ea0.record(s);
-        ea1.record(s);
     }
+    if (!ea0_recorded) ea0.record(s);
+    ea1.record(s);
     if (resident_only) {
         CK(cudaStreamSynchronize(s));
         sh.stats.ms_h2d = ms_h2d;
         return;
     }
+    const int kfirst = sh.stats.pulse_first, klast = sh.stats.pulse_last;
     if (sh.ap.npix > 0) {
         launch_finalize(sh.ap.npix, sh.ap.out_width, sh.pix.p, sh.acc.p, sh.out.p, sh.range_cor.p, hs.a.mantissa_nbits, s);
         CK(cudaGetLastError());
@@ -664,26 +875,31 @@ static void shard_download(const HostScene& hs, Shard& sh, float* out, float* he
     sh.stats.ms_d2h = elapsed(e0, e1);
 }
 
-static std::unique_ptr<I3B_Plan> make_plan(const I3B_BackprojectArgs* args)
+// `deep_copy`: a resident plan outlives the caller's descriptor arrays (orbit, LUTs, DEM raster,
+// kernel table) and keeps its own copies; the blocking one-shot call reads them in place (a
+// raster DEM is hundreds of MB).
+static std::unique_ptr<I3B_Plan> make_plan(const I3B_BackprojectArgs* args, bool deep_copy)
 {
     if (!args) throw ApiError(I3B_EXC_INVALID_ARGUMENT, "null argument block");
     validate(*args);
     std::unique_ptr<I3B_Plan> plan(new I3B_Plan());
     HostScene& hs = plan->hs;
     hs.a = *args;
-    copy_geometry(args->out_geometry, hs.out_pos, hs.out_vel, hs.out_dop, hs.a.out_geometry);
-    copy_geometry(args->in_geometry, hs.in_pos, hs.in_vel, hs.in_dop, hs.a.in_geometry);
-    if (args->dem.have_raster) {
-        hs.dem.assign(args->dem.data, args->dem.data + (size_t) args->dem.length * args->dem.width);
-        hs.a.dem.data = hs.dem.data();
-    }
-    if (args->kernel.data && args->kernel.n > 0) {
-        hs.kdata.assign(args->kernel.data, args->kernel.data + args->kernel.n);
-        hs.a.kernel.data = hs.kdata.data();
-    }
-    if (args->range_cor) {
-        hs.range_cor.assign(args->range_cor, args->range_cor + 2 * (size_t) args->out_geometry.grid.width);
-        hs.a.range_cor = hs.range_cor.data();
+    if (deep_copy) {
+        copy_geometry(args->out_geometry, hs.out_pos, hs.out_vel, hs.out_dop, hs.a.out_geometry);
+        copy_geometry(args->in_geometry, hs.in_pos, hs.in_vel, hs.in_dop, hs.a.in_geometry);
+        if (args->dem.have_raster) {
+            hs.dem.assign(args->dem.data, args->dem.data + (size_t) args->dem.length * args->dem.width);
+            hs.a.dem.data = hs.dem.data();
+        }
+        if (args->kernel.data && args->kernel.n > 0) {
+            hs.kdata.assign(args->kernel.data, args->kernel.data + args->kernel.n);
+            hs.a.kernel.data = hs.kdata.data();
+        }
+        if (args->range_cor) {
+            hs.range_cor.assign(args->range_cor, args->range_cor + 2 * (size_t) args->out_geometry.grid.width);
+            hs.a.range_cor = hs.range_cor.data();
+        }
     }
     int ndev_avail = 0;
     {
@@ -833,6 +1049,60 @@ static int guarded(F&& f)
 
 } // namespace i3b
 
+namespace {
+
+struct GeomBatch {
+    cudaStream_t s = nullptr;
+    DevBuf<double> pos, vel, lut;
+    DevBuf<float> dem;
+    DevBuf<DevStatus> status;
+    ~GeomBatch()
+    {
+        if (s) {
+            cudaStreamSynchronize(s);
+            cudaStreamDestroy(s);
+        }
+    }
+    void check_device()
+    {
+        int dev = 0, cc_major = 0;
+        CK(cudaGetDevice(&dev));
+        CK(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+        if (cc_major < 10)
+            throw ApiError(I3B_EXC_NO_DEVICE, "current device is not sm_100-class; isce3_b200 has no fallback path");
+        CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        status.alloc(1);
+        CK(cudaMemsetAsync(status.p, 0, sizeof(DevStatus), s));
+    }
+    DevOrbit orbit(const I3B_Orbit& o)
+    {
+        if (o.n < 2 || !o.pos || !o.vel) throw ApiError(I3B_EXC_INVALID_ARGUMENT, "orbit needs state vectors");
+        if (o.method != I3B_ORBIT_HERMITE && o.method != I3B_ORBIT_LEGENDRE)
+            throw ApiError(I3B_EXC_INVALID_ARGUMENT, "unknown orbit interpolation method");
+        pos.upload(o.pos, 3 * (size_t) o.n, s);
+        vel.upload(o.vel, 3 * (size_t) o.n, s);
+        return DevOrbit {o.t0, o.dt, o.n, o.method, pos.p, vel.p};
+    }
+    int finish()
+    {
+        DevStatus st;
+        CK(cudaMemcpyAsync(&st, status.p, sizeof st, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        return st.soft_error;
+    }
+};
+
+// host array -> device (or pass a device pointer through)
+template<typename T>
+const T* stage_in(DevBuf<T>& buf, const T* p, size_t n, bool devptr, cudaStream_t s)
+{
+    if (devptr || !p) return p;
+    buf.upload(p, n, s);
+    return buf.p;
+}
+
+} // namespace
+
 extern "C" {
 
 int i3b_backproject(const I3B_BackprojectArgs* args)
@@ -843,7 +1113,7 @@ int i3b_backproject(const I3B_BackprojectArgs* args)
             return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         };
         if (args && !args->out) throw ApiError(I3B_EXC_INVALID_ARGUMENT, "output array is null");
-        auto plan = make_plan(args);
+        auto plan = make_plan(args, false); // descriptors are used in place: the call blocks
         float* out = args->out;
         float* height = args->height;
         double t_setup = 0, t_solve = 0, t_run = 0, t_down = 0;
@@ -851,8 +1121,9 @@ int i3b_backproject(const I3B_BackprojectArgs* args)
         for_each_shard(*plan, [&](Shard& sh) {
             shard_setup(plan->hs, sh);
             if (single) t_setup = lap();
-            // the one-shot call streams from the caller's buffer (no deep copy of `in`)
-            shard_solve(plan->hs, sh);
+            // the one-shot call streams from the caller's buffer (no deep copy of `in`), and
+            // starts doing so while the target solve is still running
+            shard_solve_launch(plan->hs, sh);
             if (single) t_solve = lap();
             shard_run(plan->hs, sh, false);
             if (single) t_run = lap();
@@ -878,7 +1149,7 @@ int i3b_plan_create(const I3B_BackprojectArgs* args, I3B_Plan** out_plan)
     return guarded([&]() {
         if (!out_plan) throw ApiError(I3B_EXC_INVALID_ARGUMENT, "null plan pointer");
         *out_plan = nullptr;
-        auto plan = make_plan(args);
+        auto plan = make_plan(args, true);
         for_each_shard(*plan, [&](Shard& sh) {
             shard_setup(plan->hs, sh);
             shard_solve(plan->hs, sh);   // needed to know which pulses to keep resident
@@ -971,6 +1242,119 @@ int i3b_release_device_memory(void)
     return guarded([&]() {
         device_cache().release_all();
         return 0;
+    });
+}
+
+int i3b_rdr2geo_bracket_batch(const I3B_Orbit* orbit, const I3B_DEM* dem, double wavelength,
+                              int32_t look_side, const I3B_Rdr2GeoBracketParams* params, int64_t n,
+                              const double* aztime, const double* slant_range, const double* doppler,
+                              double* xyz, int32_t* status, uint32_t flags)
+{
+    return guarded([&]() {
+        if (!orbit || !dem || !params || n < 0 || (n > 0 && (!aztime || !slant_range || !xyz)))
+            throw ApiError(I3B_EXC_INVALID_ARGUMENT, "null argument");
+        if (look_side != I3B_LOOK_LEFT && look_side != I3B_LOOK_RIGHT)
+            throw ApiError(I3B_EXC_INVALID_ARGUMENT, "invalid look side");
+        if (n == 0) return 0;
+        const bool devptr = (flags & I3B_FLAG_DEVICE_POINTERS) != 0;
+        GeomBatch g;
+        g.check_device();
+        const DevOrbit o = g.orbit(*orbit);
+        DevDEM d;
+        std::memset(&d, 0, sizeof d);
+        d.have_raster = dem->have_raster; d.epsg = dem->epsg; d.method = dem->method;
+        d.length = (int) dem->length; d.width = (int) dem->width;
+        d.ref_height = dem->ref_height; d.xstart = dem->xstart; d.ystart = dem->ystart;
+        d.dx = dem->dx; d.dy = dem->dy;
+        if (dem->have_raster) {
+            if (!dem->data || dem->length < 4 || dem->width < 4)
+                throw ApiError(I3B_EXC_INVALID_ARGUMENT, "DEM raster too small");
+            if (dem->method == I3B_INTERP_SINC)
+                throw ApiError(I3B_EXC_INVALID_ARGUMENT, "sinc DEM interpolation is not supported");
+            if (!proj_setup(dem->epsg, kA, kE2, &d.proj))
+                throw ApiError(I3B_EXC_INVALID_ARGUMENT, "unknown EPSG code for a raster DEM");
+            g.dem.upload(dem->data, (size_t) dem->length * dem->width, g.s);
+            d.data = g.dem.p;
+        } else {
+            proj_setup(4326, kA, kE2, &d.proj);
+        }
+        DevBuf<double> b_t, b_r, b_f, b_x;
+        DevBuf<int> b_st;
+        const double* dt = stage_in(b_t, aztime, (size_t) n, devptr, g.s);
+        const double* dr = stage_in(b_r, slant_range, (size_t) n, devptr, g.s);
+        const double* df = stage_in(b_f, doppler, (size_t) n, devptr, g.s);
+        double* dx = xyz;
+        int* dst = status;
+        if (!devptr) {
+            b_x.alloc(3 * (size_t) n);
+            dx = b_x.p;
+            if (status) {
+                b_st.alloc((size_t) n);
+                dst = b_st.p;
+            }
+        }
+        launch_rdr2geo_batch(o, d, wavelength, look_side, *params, n, dt, dr, df, dx, dst, g.status.p, g.s);
+        CK(cudaGetLastError());
+        if (!devptr) {
+            CK(cudaMemcpyAsync(xyz, dx, 3 * (size_t) n * sizeof(double), cudaMemcpyDeviceToHost, g.s));
+            if (status) CK(cudaMemcpyAsync(status, dst, (size_t) n * sizeof(int), cudaMemcpyDeviceToHost, g.s));
+        }
+        return g.finish();
+    });
+}
+
+int i3b_geo2rdr_bracket_batch(const I3B_Orbit* orbit, const I3B_LUT2d* doppler, double wavelength,
+                              int32_t look_side, const I3B_Geo2RdrBracketParams* params, int64_t n,
+                              const double* xyz, double* aztime, double* slant_range, int32_t* status,
+                              uint32_t flags)
+{
+    return guarded([&]() {
+        if (!orbit || !doppler || !params || n < 0 || (n > 0 && (!aztime || !slant_range || !xyz)))
+            throw ApiError(I3B_EXC_INVALID_ARGUMENT, "null argument");
+        if (look_side != I3B_LOOK_LEFT && look_side != I3B_LOOK_RIGHT)
+            throw ApiError(I3B_EXC_INVALID_ARGUMENT, "invalid look side");
+        if (n == 0) return 0;
+        const bool devptr = (flags & I3B_FLAG_DEVICE_POINTERS) != 0;
+        GeomBatch g;
+        g.check_device();
+        const DevOrbit o = g.orbit(*orbit);
+        DevLUT2d l;
+        std::memset(&l, 0, sizeof l);
+        l.have_data = doppler->have_data; l.bounds_error = doppler->bounds_error; l.method = doppler->method;
+        l.length = (int) doppler->length; l.width = (int) doppler->width;
+        l.ref_value = doppler->ref_value; l.xstart = doppler->xstart; l.ystart = doppler->ystart;
+        l.dx = doppler->dx; l.dy = doppler->dy;
+        if (doppler->have_data) {
+            if (!doppler->data || doppler->length < 1 || doppler->width < 1)
+                throw ApiError(I3B_EXC_INVALID_ARGUMENT, "Doppler LUT has no data");
+            if (doppler->method == I3B_INTERP_SINC)
+                throw ApiError(I3B_EXC_INVALID_ARGUMENT, "sinc LUT2d interpolation is not supported");
+            g.lut.upload(doppler->data, (size_t) doppler->length * doppler->width, g.s);
+            l.data = g.lut.p;
+        }
+        DevBuf<double> b_x, b_t, b_r;
+        DevBuf<int> b_st;
+        const double* dx = stage_in(b_x, xyz, 3 * (size_t) n, devptr, g.s);
+        double *dt = aztime, *dr = slant_range;
+        int* dst = status;
+        if (!devptr) {
+            b_t.alloc((size_t) n);
+            b_r.alloc((size_t) n);
+            dt = b_t.p;
+            dr = b_r.p;
+            if (status) {
+                b_st.alloc((size_t) n);
+                dst = b_st.p;
+            }
+        }
+        launch_geo2rdr_batch(o, l, wavelength, look_side, *params, n, dx, dt, dr, dst, g.status.p, g.s);
+        CK(cudaGetLastError());
+        if (!devptr) {
+            CK(cudaMemcpyAsync(aztime, dt, (size_t) n * sizeof(double), cudaMemcpyDeviceToHost, g.s));
+            CK(cudaMemcpyAsync(slant_range, dr, (size_t) n * sizeof(double), cudaMemcpyDeviceToHost, g.s));
+            if (status) CK(cudaMemcpyAsync(status, dst, (size_t) n * sizeof(int), cudaMemcpyDeviceToHost, g.s));
+        }
+        return g.finish();
     });
 }
 

@@ -55,6 +55,15 @@ void launch_accumulate_generic(const AccumParams& P, const PixelRec* pix, const 
 void launch_finalize(long long npix, int out_width, const PixelRec* pix, const double2* acc, float2* out,
                      const float2* range_cor, int mantissa_nbits, cudaStream_t s);
 
+// batch geometry (solve_kernels.cu): all pointers are device pointers
+void launch_rdr2geo_batch(const DevOrbit& orbit, const DevDEM& dem, double wvl, int side,
+                          const I3B_Rdr2GeoBracketParams& prm, long long n, const double* aztime,
+                          const double* range, const double* doppler, double* xyz, int* status,
+                          DevStatus* dev_status, cudaStream_t s);
+void launch_geo2rdr_batch(const DevOrbit& orbit, const DevLUT2d& dop, double wvl, int side,
+                          const I3B_Geo2RdrBracketParams& prm, long long n, const double* xyz,
+                          double* aztime, double* range, int* status, DevStatus* dev_status, cudaStream_t s);
+
 // fast path (accumulate_fast.cu)
 // `host_kernel`: same kernel with its data pointer in HOST memory (polynomial fitting).
 bool fast_supported(const DevKernel& host_kernel, char* why, size_t why_len);

@@ -56,10 +56,21 @@ __global__ void tile_info_init_kernel(TileInfo* tiles, int n)
 // 6 CTAs/SM (<= 85 registers, a few spills): the kernel is latency-bound (FP64 transcendentals,
 // DEM loads), more resident warps beat fewer spills -- 154 registers / 3 CTAs was 32 % slower
 // on raster DEMs and 16 % on flat ones.
+//
+// One instantiation per configuration class -- raster or constant-height DEM, any Legendre
+// orbit or Hermite only, any Doppler LUT with data or none: the flags are folded into the
+// descriptors as constants, so each instantiation carries only the samplers / orbit
+// interpolators / LUT code it can reach.  (One kernel for everything was fetch-bound:
+// `no_instruction` 3.5 warps per issue cycle, profiles/r01_ncu_target_solve.md.)
+template<bool RASTER, bool LEGENDRE, bool LUT>
 __global__ void __launch_bounds__(128, 6)
-target_solve_kernel(SolveParams P, PixelRec* __restrict__ pix, float* __restrict__ height,
+target_solve_kernel(SolveParams Pin, PixelRec* __restrict__ pix, float* __restrict__ height,
                     TileInfo* __restrict__ tiles, DevStatus* status)
 {
+    SolveParams P = Pin;
+    if (!RASTER) P.dem.have_raster = 0;
+    if (!LEGENDRE) P.out_orbit.method = P.in_orbit.method = I3B_ORBIT_HERMITE;
+    if (!LUT) P.out_doppler.have_data = P.in_doppler.have_data = 0;
     const long long tid = (long long) blockIdx.x * blockDim.x + threadIdx.x;
     const long long npix = (long long) P.out_lines * P.out_width;
     int kstart = -1, kstop = -1;
@@ -239,6 +250,73 @@ __global__ void finalize_kernel(long long npix, int out_width, const PixelRec* _
     out[tid] = o;
 }
 
+// ---- batch geometry (the solvers as a reusable device API) ------------------------------
+// One thread per point; same device functions as the target solve above.  These replace, for
+// array callers, what the reference exposes per thread in cuda/geometry/gpuGeometry.cu:57-68
+// (rdr2geo_bracket) and :166-181 (geo2rdr_bracket) on top of device-side `new` + virtual
+// dispatch (gpuDEMInterpolator.cu:69-90): here the DEM / LUT / orbit are POD descriptors.
+__global__ void __launch_bounds__(128)
+rdr2geo_batch_kernel(DevOrbit orbit, DevDEM dem, double wvl, int side, I3B_Rdr2GeoBracketParams prm,
+                     long long n, const double* __restrict__ aztime, const double* __restrict__ range,
+                     const double* __restrict__ doppler, double* __restrict__ xyz,
+                     int* __restrict__ status, DevStatus* dev_status)
+{
+    const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    D3 x = nan3();
+    int st = rdr2geo_bracket(aztime[i], range[i], doppler ? doppler[i] : 0.0, orbit, dem, wvl, side, prm, &x);
+    if (st == I3B_EXC_OUT_OF_RANGE) {
+        // (the CPU reference throws OutOfRange here, core/Orbit.cpp:78-83; per point: a domain error code)
+        st = I3B_ORBIT_INTERP_DOMAIN_ERROR;
+        x = nan3();
+    } else if (st != I3B_SUCCESS) {
+        x = nan3();
+    }
+    xyz[3 * i] = x.x;
+    xyz[3 * i + 1] = x.y;
+    xyz[3 * i + 2] = x.z;
+    if (status) status[i] = st;
+    if (st != I3B_SUCCESS) dev_status->soft_error = st;
+}
+
+__global__ void __launch_bounds__(128)
+geo2rdr_batch_kernel(DevOrbit orbit, DevLUT2d dop, double wvl, int side, I3B_Geo2RdrBracketParams prm,
+                     long long n, const double* __restrict__ xyz, double* __restrict__ aztime,
+                     double* __restrict__ range, int* __restrict__ status, DevStatus* dev_status)
+{
+    const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const D3 x = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
+    double t = nan(""), r = nan("");
+    const int st = geo2rdr_bracket(x, orbit, dop, wvl, side, prm, &t, &r);
+    if (st != I3B_SUCCESS) {
+        t = r = nan("");
+        dev_status->soft_error = st;
+    }
+    aztime[i] = t;
+    range[i] = r;
+    if (status) status[i] = st;
+}
+
+void launch_rdr2geo_batch(const DevOrbit& orbit, const DevDEM& dem, double wvl, int side,
+                          const I3B_Rdr2GeoBracketParams& prm, long long n, const double* aztime,
+                          const double* range, const double* doppler, double* xyz, int* status,
+                          DevStatus* dev_status, cudaStream_t s)
+{
+    if (n <= 0) return;
+    rdr2geo_batch_kernel<<<(unsigned) ((n + 127) / 128), 128, 0, s>>>(orbit, dem, wvl, side, prm, n, aztime, range,
+                                                                     doppler, xyz, status, dev_status);
+}
+
+void launch_geo2rdr_batch(const DevOrbit& orbit, const DevLUT2d& dop, double wvl, int side,
+                          const I3B_Geo2RdrBracketParams& prm, long long n, const double* xyz,
+                          double* aztime, double* range, int* status, DevStatus* dev_status, cudaStream_t s)
+{
+    if (n <= 0) return;
+    geo2rdr_batch_kernel<<<(unsigned) ((n + 127) / 128), 128, 0, s>>>(orbit, dop, wvl, side, prm, n, xyz, aztime, range,
+                                                                     status, dev_status);
+}
+
 // ---- launchers -------------------------------------------------------------------------
 
 void launch_pulse_table(const DevOrbit& orbit, Linspace in_time, double fc, PulseRec* pulse,
@@ -255,7 +333,23 @@ void launch_target_solve(const SolveParams& P, PixelRec* pix, float* height, Til
     const long long npix = (long long) P.out_lines * P.out_width;
     if (npix == 0) return;
     const unsigned grid = (unsigned) ((npix + 127) / 128);
-    target_solve_kernel<<<grid, 128, 0, s>>>(P, pix, height, tiles, status);
+    const bool raster = P.dem.have_raster != 0;
+    const bool legendre = P.out_orbit.method == I3B_ORBIT_LEGENDRE || P.in_orbit.method == I3B_ORBIT_LEGENDRE;
+    const bool lut = P.out_doppler.have_data || P.in_doppler.have_data;
+    const int cls = (raster ? 4 : 0) | (legendre ? 2 : 0) | (lut ? 1 : 0);
+#define I3B_SOLVE_CASE(C, R, L, U) \
+    case C: target_solve_kernel<R, L, U><<<grid, 128, 0, s>>>(P, pix, height, tiles, status); break
+    switch (cls) {
+        I3B_SOLVE_CASE(0, false, false, false);
+        I3B_SOLVE_CASE(1, false, false, true);
+        I3B_SOLVE_CASE(2, false, true, false);
+        I3B_SOLVE_CASE(3, false, true, true);
+        I3B_SOLVE_CASE(4, true, false, false);
+        I3B_SOLVE_CASE(5, true, false, true);
+        I3B_SOLVE_CASE(6, true, true, false);
+        I3B_SOLVE_CASE(7, true, true, true);
+    }
+#undef I3B_SOLVE_CASE
 }
 
 void launch_accumulate_generic(const AccumParams& P, const PixelRec* pix, const double* pv,

@@ -47,3 +47,62 @@ class DEMInterpolator:
     @property
     def length(self):
         return 0 if self.data is None else self.data.shape[0]
+
+
+# ---- per-point geometry on the GPU (batch API of include/isce3_b200_backproject.h) ---------
+
+def rdr2geo_bracket(aztime, slant_range, doppler, orbit, dem, wavelength, side,
+                    tol_height=1e-5, look_min=0.0, look_max=np.pi / 2):
+    """Arrays of radar coordinates -> target ECEF positions on the DEM, per point like
+    ``isce3.geometry.rdr2geo_bracket`` (geometry/rdr2geo_roots.cpp:14-27,
+    python/extensions/pybind_isce3/geometry/rdr2geo_roots.cpp): returns ``(xyz[n,3], status[n])``
+    with ``status`` the per-point ErrorCode (0 = converged; failed points are NaN)."""
+    import ctypes as C
+
+    from . import _capi
+    from .focus import raise_for_status
+    t = np.ascontiguousarray(np.atleast_1d(aztime), dtype=np.float64)
+    r = np.ascontiguousarray(np.broadcast_to(np.asarray(slant_range, np.float64), t.shape))
+    fd = None if doppler is None else np.ascontiguousarray(np.broadcast_to(np.asarray(doppler, np.float64), t.shape))
+    n = t.size
+    xyz = np.empty((n, 3), np.float64)
+    status = np.empty(n, np.int32)
+    fl = _capi.Flattened()
+    o = _capi.flatten_orbit(orbit, fl)
+    d = _capi.flatten_dem(dem, fl)
+    prm = _capi.Rdr2GeoBracketParams(tol_height, look_min, look_max)
+    lib = _capi.load_library()
+    rc = lib.i3b_rdr2geo_bracket_batch(C.byref(o), C.byref(d), C.c_double(wavelength), int(side), C.byref(prm),
+                                       C.c_int64(n), t.ctypes.data, r.ctypes.data,
+                                       fd.ctypes.data if fd is not None else None, xyz.ctypes.data,
+                                       status.ctypes.data, 0)
+    if rc < 0:
+        raise_for_status(rc, (lib.i3b_last_error() or b"").decode())
+    return xyz, status
+
+
+def geo2rdr_bracket(xyz, orbit, doppler, wavelength, side, tol_aztime=1e-7, time_start=None,
+                    time_end=None):
+    """Arrays of ECEF targets -> (aztime[n], slant_range[n], status[n]), per point like
+    ``isce3.geometry.geo2rdr_bracket`` (geometry/geo2rdr_roots.cpp:16-25)."""
+    import ctypes as C
+
+    from . import _capi
+    from .focus import raise_for_status
+    x = np.ascontiguousarray(np.asarray(xyz, np.float64).reshape(-1, 3))
+    n = x.shape[0]
+    t = np.empty(n, np.float64)
+    r = np.empty(n, np.float64)
+    status = np.empty(n, np.int32)
+    fl = _capi.Flattened()
+    o = _capi.flatten_orbit(orbit, fl)
+    lut = _capi.flatten_lut2d(doppler, fl)
+    prm = _capi.Geo2RdrBracketParams(tol_aztime, int(time_start is not None), int(time_end is not None),
+                                     time_start or 0.0, time_end or 0.0)
+    lib = _capi.load_library()
+    rc = lib.i3b_geo2rdr_bracket_batch(C.byref(o), C.byref(lut), C.c_double(wavelength), int(side), C.byref(prm),
+                                       C.c_int64(n), x.ctypes.data, t.ctypes.data, r.ctypes.data,
+                                       status.ctypes.data, 0)
+    if rc < 0:
+        raise_for_status(rc, (lib.i3b_last_error() or b"").decode())
+    return t, r, status
