@@ -308,6 +308,25 @@ int i3b_plan_execute(I3B_Plan* plan);
 int i3b_plan_download(I3B_Plan* plan, float* out, float* height);
 int i3b_plan_destroy(I3B_Plan* plan);
 
+/* Blocks API: ONE swath, MANY output blocks.  The workflow cuts the image
+ * into blocks and calls backproject once per block with the whole swath pointer
+ * (nisar/workflows/focus.py:726-783, :1988-2007); i3b_blocks_create uploads the swath, DEM,
+ * LUTs and per-pulse tables ONCE to every listed device, i3b_blocks_run focuses any number of
+ * blocks from there -- free devices take the next block -- writing each into its own host
+ * array, exactly what the per-block calls would have produced.
+ *   args: as for i3b_backproject; `out` / `height` are ignored, out_geometry supplies the
+ *         orbit and Doppler LUT of the output grids (its grid is the whole image: range_cor,
+ *         if given, holds that image's columns).
+ *   grids[i]: output sub-grid of block i (sensing_start / starting_range already those of
+ *         the block, as RadarGridParameters slicing gives them); out[i]: complex64
+ *         [length][width]; height: NULL or height[i] float32 [length][width] (entries may be
+ *         NULL).                                                                        */
+typedef struct I3B_Blocks I3B_Blocks;
+int i3b_blocks_create(const I3B_BackprojectArgs* args, I3B_Blocks** blocks);
+int i3b_blocks_run(I3B_Blocks* blocks, int32_t n, const I3B_RadarGrid* grids, float* const* out,
+                   float* const* height);
+int i3b_blocks_destroy(I3B_Blocks* blocks);
+
 int i3b_last_stats(I3B_Stats* stats);
 const char* i3b_last_error(void);
 const char* i3b_version(void);

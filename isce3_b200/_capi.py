@@ -245,6 +245,9 @@ EXPORTED_SYMBOLS = (
     "i3b_measure_peaks",
     "i3b_fit_tap_polynomials",
     "i3b_release_device_memory",
+    "i3b_blocks_create",
+    "i3b_blocks_run",
+    "i3b_blocks_destroy",
     "i3b_rdr2geo_bracket_batch",
     "i3b_geo2rdr_bracket_batch",
     "i3b_rangecomp_create",
@@ -298,6 +301,13 @@ def load_library() -> C.CDLL:
     lib.i3b_fit_tap_polynomials.restype = C.c_int
     lib.i3b_release_device_memory.restype = C.c_int
     lib.i3b_current_device.restype = C.c_int
+    lib.i3b_blocks_create.argtypes = [C.POINTER(BackprojectArgs), C.POINTER(C.c_void_p)]
+    lib.i3b_blocks_create.restype = C.c_int
+    lib.i3b_blocks_run.argtypes = [C.c_void_p, C.c_int32, C.POINTER(RadarGrid), C.POINTER(C.c_void_p),
+                                   C.POINTER(C.c_void_p)]
+    lib.i3b_blocks_run.restype = C.c_int
+    lib.i3b_blocks_destroy.argtypes = [C.c_void_p]
+    lib.i3b_blocks_destroy.restype = C.c_int
     lib.i3b_rdr2geo_bracket_batch.argtypes = [
         C.POINTER(Orbit), C.POINTER(DEM), C.c_double, C.c_int32, C.POINTER(Rdr2GeoBracketParams), C.c_int64,
         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]

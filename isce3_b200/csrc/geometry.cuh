@@ -115,9 +115,12 @@ __device__ inline void orbit_legendre(const DevOrbit& o, double t, D3* pos, D3* 
     *vel = v;
 }
 
+// LEG = false: the caller knows (at compile time) that no orbit on its path is Legendre
+template<bool LEG = true>
 __device__ inline int orbit_interpolate(const DevOrbit& o, double t, int border, D3* pos, D3* vel)
 {
-    const int need = o.method == I3B_ORBIT_LEGENDRE ? 9 : 4;
+    const int method = LEG ? o.method : (int) I3B_ORBIT_HERMITE;
+    const int need = method == I3B_ORBIT_LEGENDRE ? 9 : 4;
     if (o.n < need) return I3B_ORBIT_INTERP_SIZE_ERROR;
     const double tstart = o.t0, tend = o.t0 + (o.n - 1) * o.dt;
     if (t < tstart || t > tend) {
@@ -127,11 +130,11 @@ __device__ inline int orbit_interpolate(const DevOrbit& o, double t, int border,
         }
         if (border != BORDER_EXTRAPOLATE) return I3B_ORBIT_INTERP_DOMAIN_ERROR;
     }
-    if (o.method == I3B_ORBIT_HERMITE) {
+    if (method == I3B_ORBIT_HERMITE) {
         orbit_hermite(o, t, pos, vel);
         return I3B_SUCCESS;
     }
-    if (o.method == I3B_ORBIT_LEGENDRE) {
+    if (LEG && method == I3B_ORBIT_LEGENDRE) {
         orbit_legendre(o, t, pos, vel);
         return I3B_SUCCESS;
     }
@@ -334,9 +337,11 @@ __device__ inline U interp2d(int method, double x, double y, const G& z)
     }
 }
 
+// LUT = false: the caller knows that no Doppler LUT on its path holds data
+template<bool LUT = true>
 __device__ inline double lut2d_eval(const DevLUT2d& l, double y, double x)
 {
-    if (!l.have_data) return l.ref_value;
+    if (!LUT || !l.have_data) return l.ref_value;
     double xi = (x - l.xstart) / l.dx;
     double yi = (y - l.ystart) / l.dy;
     xi = fmin(fmax(xi, 0.0), l.width - 1.0);
@@ -461,12 +466,13 @@ __device__ inline int brent(double a, double b, F f, const double tol, double* r
 // Target ECEF on the DEM for (aztime, range, doppler).  Returns I3B_SUCCESS, a soft
 // ErrorCode, or I3B_EXC_OUT_OF_RANGE when aztime is outside the orbit (the CPU
 // reference throws there, core/Orbit.cpp:78-83).
+template<bool RASTER = true, bool LEG = true>
 __device__ inline int rdr2geo_bracket(double aztime, double slant_range, double doppler,
                                       const DevOrbit& orbit, const DevDEM& dem, double wavelength,
                                       int side, const I3B_Rdr2GeoBracketParams& prm, D3* xyz)
 {
     D3 radar, velocity;
-    if (orbit_interpolate(orbit, aztime, BORDER_ERROR, &radar, &velocity) != I3B_SUCCESS)
+    if (orbit_interpolate<LEG>(orbit, aztime, BORDER_ERROR, &radar, &velocity) != I3B_SUCCESS)
         return I3B_EXC_OUT_OF_RANGE;
     const double speed = norm(velocity);
     const D3 along = velocity / speed;
@@ -484,7 +490,7 @@ __device__ inline int rdr2geo_bracket(double aztime, double slant_range, double 
     };
     const double tol_look = prm.tol_height / radius;
     double look = 0.0;
-    if (!dem.have_raster) {
+    if (!RASTER || !dem.have_raster) {
         // Constant-height DEM: the height error is monotonic in the look angle, so the root in
         // [look_min, look_max] is unique.  Bracket it tightly around the spherical-Earth
         // solution first (same root finder, same tolerance: the result is the root to within
@@ -543,6 +549,7 @@ __device__ inline int rdr2geo_bracket(double aztime, double slant_range, double 
 // finder and tolerance as the reference, so the answer is the root to within tol_aztime
 // either way -- and the reference's full interval is the fallback (also taken when the
 // guess is NaN).
+template<bool LEG = true, bool LUT = true>
 __device__ inline int geo2rdr_bracket(D3 x, const DevOrbit& orbit, const DevLUT2d& dop,
                                       double wavelength, int side,
                                       const I3B_Geo2RdrBracketParams& prm, double* aztime,
@@ -550,16 +557,17 @@ __device__ inline int geo2rdr_bracket(D3 x, const DevOrbit& orbit, const DevLUT2
 {
     const double orbit_start = orbit.t0, orbit_end = orbit.t0 + (orbit.n - 1) * orbit.dt;
     double t0, t1;
+    const bool have_lut = LUT && dop.have_data;
     if (prm.has_time_start) t0 = prm.time_start;
-    else t0 = dop.have_data ? fmax(orbit_start, dop.ystart) : orbit_start;
+    else t0 = have_lut ? fmax(orbit_start, dop.ystart) : orbit_start;
     if (prm.has_time_end) t1 = prm.time_end;
-    else t1 = dop.have_data ? fmin(orbit_end, dop.ystart + dop.dy * (dop.length - 1)) : orbit_end;
+    else t1 = have_lut ? fmin(orbit_end, dop.ystart + dop.dy * (dop.length - 1)) : orbit_end;
     D3 xp, v, r;
     auto doppler_error = [&](double t) {
-        orbit_interpolate(orbit, t, BORDER_FILLNAN, &xp, &v);
+        orbit_interpolate<LEG>(orbit, t, BORDER_FILLNAN, &xp, &v);
         r = x - xp;
         const double rnorm = norm(r);
-        const double fd = lut2d_eval(dop, t, rnorm);
+        const double fd = lut2d_eval<LUT>(dop, t, rnorm);
         return 2.0 / wavelength * dot(v, r) / rnorm - fd;
     };
     int err = I3B_INVALID_INTERVAL;
@@ -583,7 +591,7 @@ __device__ inline int geo2rdr_bracket(D3 x, const DevOrbit& orbit, const DevLUT2
     }
     if (err != I3B_SUCCESS) err = brent(t0, t1, doppler_error, prm.tol_aztime, aztime);
     if (err != I3B_SUCCESS) return err;
-    orbit_interpolate(orbit, *aztime, BORDER_FILLNAN, &xp, &v);
+    orbit_interpolate<LEG>(orbit, *aztime, BORDER_FILLNAN, &xp, &v);
     r = x - xp;
     *range = norm(r);
     const bool positive = dot(cross(r, v), xp) > 0;

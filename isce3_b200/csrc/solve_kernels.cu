@@ -58,19 +58,15 @@ __global__ void tile_info_init_kernel(TileInfo* tiles, int n)
 // on raster DEMs and 16 % on flat ones.
 //
 // One instantiation per configuration class -- raster or constant-height DEM, any Legendre
-// orbit or Hermite only, any Doppler LUT with data or none: the flags are folded into the
-// descriptors as constants, so each instantiation carries only the samplers / orbit
-// interpolators / LUT code it can reach.  (One kernel for everything was fetch-bound:
+// orbit or Hermite only, any Doppler LUT with data or none: the flags are template arguments
+// of the solvers, so each instantiation carries only the samplers / orbit interpolators / LUT
+// code it can reach.  (One kernel for everything was fetch-bound:
 // `no_instruction` 3.5 warps per issue cycle, profiles/r01_ncu_target_solve.md.)
 template<bool RASTER, bool LEGENDRE, bool LUT>
 __global__ void __launch_bounds__(128, 6)
-target_solve_kernel(SolveParams Pin, PixelRec* __restrict__ pix, float* __restrict__ height,
+target_solve_kernel(SolveParams P, PixelRec* __restrict__ pix, float* __restrict__ height,
                     TileInfo* __restrict__ tiles, DevStatus* status)
 {
-    SolveParams P = Pin;
-    if (!RASTER) P.dem.have_raster = 0;
-    if (!LEGENDRE) P.out_orbit.method = P.in_orbit.method = I3B_ORBIT_HERMITE;
-    if (!LUT) P.out_doppler.have_data = P.in_doppler.have_data = 0;
     const long long tid = (long long) blockIdx.x * blockDim.x + threadIdx.x;
     const long long npix = (long long) P.out_lines * P.out_width;
     int kstart = -1, kstop = -1;
@@ -79,20 +75,20 @@ target_solve_kernel(SolveParams Pin, PixelRec* __restrict__ pix, float* __restri
         const int i = (int) (tid % P.out_width);
         const double t = P.out_time[j];
         const double r = P.out_range[i];
-        const double fD = lut2d_eval(P.out_doppler, t, r);
+        const double fD = lut2d_eval<LUT>(P.out_doppler, t, r);
         // LUT2d with bounds_error (LUT2d.cpp:143-150): the CPU reference raises through its
         // error channel, the reference CUDA path silently returns ref_value
         // (gpuLUT2d.cu:178-181).  Here the lookup is clamped like bounds_error=False and the
         // call reports the soft code OutOfBoundsLookup (checked at the solutions, not at the
         // probes of the root finders).
-        if (P.out_doppler.bounds_error && !lut2d_contains(P.out_doppler, t, r))
+        if (LUT && P.out_doppler.bounds_error && !lut2d_contains(P.out_doppler, t, r))
             status->soft_error = I3B_OUT_OF_BOUNDS_LOOKUP;
         PixelRec rec;
         rec.x = rec.y = rec.z = nan("");
         rec.tau_atm = 0.0;
         float h = nanf("");
         D3 x;
-        int st = rdr2geo_bracket(t, r, fD, P.out_orbit, P.dem, P.wvl, P.out_side, P.r2g, &x);
+        int st = rdr2geo_bracket<RASTER, LEGENDRE>(t, r, fD, P.out_orbit, P.dem, P.wvl, P.out_side, P.r2g, &x);
         if (st == I3B_EXC_OUT_OF_RANGE) {
             status->hard_error = st;
         } else if (st != I3B_SUCCESS) {
@@ -101,14 +97,14 @@ target_solve_kernel(SolveParams Pin, PixelRec* __restrict__ pix, float* __restri
             const D3 llh = xyz_to_llh(x);
             h = (float) llh.z;
             double tc, rc;
-            st = geo2rdr_bracket(x, P.in_orbit, P.in_doppler, P.wvl, P.in_side, P.g2r, &tc, &rc, t);
+            st = geo2rdr_bracket<LEGENDRE, LUT>(x, P.in_orbit, P.in_doppler, P.wvl, P.in_side, P.g2r, &tc, &rc, t);
             if (st != I3B_SUCCESS) {
                 status->soft_error = I3B_FAILED_TO_CONVERGE;
             } else {
-                if (P.in_doppler.bounds_error && !lut2d_contains(P.in_doppler, tc, rc))
+                if (LUT && P.in_doppler.bounds_error && !lut2d_contains(P.in_doppler, tc, rc))
                     status->soft_error = I3B_OUT_OF_BOUNDS_LOOKUP;
                 D3 p, v;
-                orbit_interpolate(P.in_orbit, tc, BORDER_FILLNAN, &p, &v);
+                orbit_interpolate<LEGENDRE>(P.in_orbit, tc, BORDER_FILLNAN, &p, &v);
                 const double l = P.wvl * rc * (norm(p) / norm(x)) / (2. * P.ds);
                 const double cpi = l / norm(v);
                 const double tstart = tc - 0.5 * cpi, tstop = tc + 0.5 * cpi;

@@ -276,6 +276,72 @@ class BackprojectPlan:
             pass
 
 
+class BlockFocuser:
+    """One swath, many output blocks (i3b_blocks_*): what the workflow does with one
+    ``backproject`` call per block and the whole swath pointer each time
+    (nisar/workflows/focus.py:726-783, :1988-2007), with the swath, DEM, LUTs and per-pulse
+    tables uploaded ONCE per device.  ``out_geometry`` is the geometry of the whole image
+    (orbit and Doppler LUT are shared by every block); ``run`` takes the blocks as
+    ``(radar_grid_of_the_block, out_array[, height_array])`` and hands them to the listed devices
+    dynamically.  Returns True if any pixel failed (like ``backproject``)."""
+
+    def __init__(self, out_geometry, in_, in_geometry, dem, fc, ds, kernel, dry_tropo_model="tsx",
+                 rdr2geo_params=None, geo2rdr_params=None, devices=None, force_generic=False,
+                 range_cor=None, mantissa_nbits=None):
+        self._lib = _capi.load_library()
+        self._fl = build_args(None, out_geometry, in_, in_geometry, dem, fc, ds, kernel, dry_tropo_model,
+                              rdr2geo_params, geo2rdr_params, 1024, None, devices, force_generic,
+                              range_cor, mantissa_nbits)
+        self._handle = C.c_void_p()
+        status = self._lib.i3b_blocks_create(C.byref(self._fl.args), C.byref(self._handle))
+        if status < 0:
+            raise_for_status(status, (self._lib.i3b_last_error() or b"").decode())
+
+    def run(self, blocks) -> bool:
+        blocks = list(blocks)
+        n = len(blocks)
+        grids = (_capi.RadarGrid * max(n, 1))()
+        outs = (C.c_void_p * max(n, 1))()
+        heights = (C.c_void_p * max(n, 1))()
+        any_height = False
+        for i, blk in enumerate(blocks):
+            grid, out = blk[0], blk[1]
+            height = blk[2] if len(blk) > 2 else None
+            grid = getattr(grid, "radar_grid", grid)
+            shape = (grid.length, grid.width)
+            _check_array(out, "output", np.complex64, shape, "output array")
+            grids[i] = _capi.flatten_grid(grid)
+            outs[i] = out.ctypes.data
+            if height is not None:
+                _check_array(height, "height", np.float32, shape, "height array")
+                heights[i] = height.ctypes.data
+                any_height = True
+        status = self._lib.i3b_blocks_run(self._handle, n, grids, outs, heights if any_height else None)
+        if status < 0:
+            raise_for_status(status, (self._lib.i3b_last_error() or b"").decode())
+        return status != _capi.SUCCESS
+
+    def stats(self) -> dict:
+        return last_stats()
+
+    def close(self):
+        if self._handle:
+            self._lib.i3b_blocks_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def release_device_memory() -> None:
     """Hand the device memory cached by earlier calls back to the driver."""
     _capi.load_library().i3b_release_device_memory()

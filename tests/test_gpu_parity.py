@@ -672,3 +672,48 @@ def test_empty_and_tiny_grids():
     sc.out_geometry = RadarGeometry(g, sc.out_geometry.orbit, LUT2d())
     out = np.zeros((0, 1), np.complex64)
     assert backproject(out, *sc.backproject_args()) is False
+
+
+def test_blocks_api_equals_per_block_calls(oracle):
+    """i3b_blocks_*: the swath and every table uploaded once, output blocks focused from there
+    (the workflow's per-block loop, focus.py:1988-2007).  Full-width blocks cut on tile rows
+    reproduce the whole-image call bit for bit; arbitrary blocks (range splits, ragged sizes)
+    equal their own per-block backproject() call bit for bit, and the range_cor phasors follow
+    the block's columns."""
+    from isce3_b200.focus import BlockFocuser
+    sc = synth.make_scene("c2", pulses=3072, bins=1024, out_lines=44, out_samples=300, n_targets=2)
+    grid = sc.out_geometry.radar_grid
+    whole = run_gpu(sc)
+    common = sc.backproject_args()
+    with BlockFocuser(*common, devices=[0, 0]) as bf:
+        # (a) full-width blocks of 12 lines (a multiple of the 4-line tile rows)
+        blocks, image = [], np.zeros(shape_of(sc), np.complex64)
+        heights = np.zeros(shape_of(sc), np.float32)
+        for a0 in range(0, 44, 12):
+            a1 = min(a0 + 12, 44)
+            blocks.append((grid[a0:a1, :], image[a0:a1], heights[a0:a1]))
+        assert bf.run(blocks) is False
+        st = bf.stats()
+        assert st["pixel_pulses"] == whole[3]["pixel_pulses"] and st["used_fast_kernel"] == 1
+        np.testing.assert_array_equal(image, whole[1])
+        np.testing.assert_array_equal(heights, whole[2])
+        # (b) ragged blocks with range splits: each equals its own one-shot call
+        cuts = [(0, 17, 0, 130), (0, 17, 130, 300), (17, 44, 0, 77), (17, 44, 77, 300)]
+        outs = [np.zeros((a1 - a0, r1 - r0), np.complex64) for a0, a1, r0, r1 in cuts]
+        assert bf.run([(grid[a0:a1, r0:r1], o) for (a0, a1, r0, r1), o in zip(cuts, outs)]) is False
+        for (a0, a1, r0, r1), o in zip(cuts, outs):
+            single = np.zeros_like(o)
+            backproject(single, sc.out_subgrid(a0, a1, r0, r1), *common[1:])
+            np.testing.assert_array_equal(o, single)
+            assert np.linalg.norm(o - whole[1][a0:a1, r0:r1]) <= 1e-5 * np.linalg.norm(o)
+    cpu = run_cpu(oracle, sc)
+    check((whole[0], image, heights, whole[3]), cpu, sc)
+    # (c) per-column output phasors follow the block's columns
+    rng = np.random.default_rng(3)
+    cor = np.exp(2j * np.pi * rng.uniform(size=300)).astype(np.complex64)
+    with BlockFocuser(*common, range_cor=cor) as bf:
+        o = np.zeros((10, 100), np.complex64)
+        bf.run([(grid[8:18, 150:250], o)])
+    want = np.zeros((10, 100), np.complex64)
+    backproject(want, sc.out_subgrid(8, 18, 150, 250), *common[1:], range_cor=cor[150:250])
+    np.testing.assert_array_equal(o, want)
