@@ -158,6 +158,8 @@ struct FastParams {
     int n_pulses;   // pulses in the input grid (size of the pulse table)
     int W;          // staged samples per pulse (even, <= 256)
     int tiles_rg, tiles_az;
+    int tile_j0;    // first tile row of this launch (tiles_az counts the rows of the launch)
+    int k_landed;   // pulses below this index are on the device (0: no such limit)
     double G;       // samples per cycle: 1 / (fc * dtau)
     double U0;      // swst / dtau
     double fc;
@@ -829,6 +831,7 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, const __grid_
         const int gcols = min(GROUP_RG, P.tiles_rg - grp * GROUP_RG);
         tile_j = rem / gcols;
         tile_i = grp * GROUP_RG + rem - tile_j * gcols;
+        tile_j += P.tile_j0;
     }
     const int tile_id = tile_j * P.tiles_rg + tile_i; // row-major id (target-solve tile table)
     const int col0 = tile_i * TILE_RG, line0 = tile_j * TILE_AZ;
@@ -837,6 +840,12 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, const __grid_
         // job): leave before touching the pixel records
         const TileInfo ti = tiles[tile_id];
         if (ti.bad || ti.kmax <= P.k_begin || ti.kmin >= P.k_end || ti.kmin >= ti.kmax) return;
+        if (P.k_landed > 0 && min(ti.kmax, P.k_end) > P.k_landed) {
+            // the host's bound on this row's aperture did not hold: nothing of the tile is
+            // integrated, the call is redone once every pulse is on the device
+            if (threadIdx.x == 0) status->premature = 1;
+            return;
+        }
     }
 
     constexpr int LOWOFF = (K & 1) ? -(K / 2) : 1 - K / 2;
@@ -1296,6 +1305,35 @@ static FitResult fit_kernel(const DevKernel& k, double tol)
 
 constexpr double FIT_TOL = 3e-5;
 
+// The fit costs a fraction of a millisecond and a call issues several launches: remember the
+// last one per thread, keyed by the kernel's descriptor and a hash of its table.
+static const FitResult& cached_fit(const DevKernel& k)
+{
+    struct Key {
+        int kind, n, taps;
+        double halfwidth, bandwidth;
+        unsigned long long hash;
+        bool operator==(const Key& o) const
+        {
+            return kind == o.kind && n == o.n && taps == o.taps && halfwidth == o.halfwidth &&
+                   bandwidth == o.bandwidth && hash == o.hash;
+        }
+    };
+    thread_local Key last_key {-1, 0, 0, 0.0, 0.0, 0ull};
+    thread_local FitResult last_fit;
+    unsigned long long h = 1469598103934665603ull;
+    if (k.data && k.n > 0) {
+        const unsigned char* b = reinterpret_cast<const unsigned char*>(k.data);
+        for (size_t i = 0; i < (size_t) k.n * sizeof(float); ++i) h = (h ^ b[i]) * 1099511628211ull;
+    }
+    const Key key {k.kind, k.n, k.taps, k.halfwidth, k.bandwidth, h};
+    if (!(key == last_key)) {
+        last_fit = fit_kernel(k, FIT_TOL);
+        last_key = key;
+    }
+    return last_fit;
+}
+
 // instantiated tap counts: every width up to 13 (a thread keeps all K weights and the K+1
 // sample window in registers), then 16 and 32 (chunked MAC)
 static bool taps_supported(int K) { return (K >= 3 && K <= 13) || K == 16 || K == 32; }
@@ -1435,7 +1473,7 @@ int launch_accumulate_fast(const AccumParams& P, const DevKernel& hk, const Pixe
     // the magic-number splits need |fc*tau| and |u| below 2^28
     if (P.fc * (P.swst + (P.nr + 64) * P.dtau) > 2.6e8 || P.nr > (1 << 27)) return -1;
     if (!taps_supported(hk.taps)) return -1;
-    const FitResult R = fit_kernel(hk, FIT_TOL);
+    const FitResult& R = cached_fit(hk);
     if (!R.ok) return -1;
     const int K = hk.taps;
     int W = (int) std::ceil(TILE_RG * std::fabs(out_in_spacing_ratio) * 1.002) + K + 16;
@@ -1468,7 +1506,13 @@ int launch_accumulate_fast(const AccumParams& P, const DevKernel& hk, const Pixe
     FP.n_pulses = n_pulses;
     FP.W = W;
     FP.tiles_rg = (P.out_width + TILE_RG - 1) / TILE_RG;
-    FP.tiles_az = (P.out_lines + TILE_AZ - 1) / TILE_AZ;
+    {
+        const int line_end = P.line_end > 0 ? std::min(P.line_end, P.out_lines) : P.out_lines;
+        FP.tile_j0 = P.line_begin / TILE_AZ;
+        FP.tiles_az = (line_end + TILE_AZ - 1) / TILE_AZ - FP.tile_j0;
+        if (FP.tiles_az <= 0) return 0;
+    }
+    FP.k_landed = P.k_landed;
     FP.G = 1.0 / (P.fc * P.dtau);
     FP.U0 = P.swst / P.dtau;
     FP.fc = P.fc;

@@ -571,12 +571,42 @@ static void shard_solve(const HostScene& hs, Shard& sh)
 // Pulses the shard's block can possibly integrate, from host-side bounds alone (output line
 // times +- half the longest coherent processing interval of Backproject.cpp:176-193, plus the
 // beam-centre shift the Doppler LUTs allow): what the one-shot call starts uploading WHILE the
-// target solve runs.  The solve's exact range is checked against it afterwards.
-static bool conservative_pulse_range(const HostScene& hs, const Shard& sh, int* k0, int* k1)
+// target solve runs, and how it decides which output rows have all their pulses on the device.
+// The solve's exact range is checked against it afterwards (and every tile checks its own).
+struct PulseBound {
+    bool ok = false;
+    double cpi = 0, shift = 0;      // s
+    double t_out0 = 0, out_prf = 0; // output line times of the shard: t_out0 + row / out_prf
+    double t_in0 = 0, in_prf = 0;
+    int n_pulses = 0, nlines = 0;
+    // first pulse rows >= row can need / one past the last pulse rows < row_end can need
+    int lower(int row) const
+    {
+        const double lo = (t_out0 + row / out_prf - 0.5 * cpi - shift - t_in0) * in_prf - 64.0;
+        return (int) std::max(0.0, std::min(std::floor(lo), (double) n_pulses));
+    }
+    int upper(int row_end) const
+    {
+        const double hi = (t_out0 + (row_end - 1) / out_prf + 0.5 * cpi + shift - t_in0) * in_prf + 64.0;
+        return (int) std::max(0.0, std::min(std::ceil(hi), (double) n_pulses));
+    }
+    // leading rows whose pulses all lie below `landed`
+    int rows_ready(int landed) const
+    {
+        if (landed >= upper(nlines)) return nlines;
+        const double r = ((landed - 64.0) / in_prf + t_in0 - 0.5 * cpi - shift - t_out0) * out_prf;
+        int rows = (int) std::max(0.0, std::min(std::floor(r) + 1.0, (double) nlines));
+        while (rows > 0 && upper(rows) > landed) --rows; // (rounding)
+        return rows;
+    }
+};
+
+static PulseBound conservative_pulse_bound(const HostScene& hs, const Shard& sh)
 {
+    PulseBound B;
     const I3B_BackprojectArgs& a = hs.a;
     const I3B_RadarGrid &og = a.out_geometry.grid, &ig = a.in_geometry.grid;
-    if (sh.nlines <= 0 || og.width <= 0 || ig.length <= 0) return false;
+    if (sh.nlines <= 0 || og.width <= 0 || ig.length <= 0 || !(og.prf > 0)) return B;
     const I3B_Orbit& orb = a.in_geometry.orbit;
     double pmax = 0, vmin = 1e300;
     for (int i = 0; i < orb.n; ++i) {
@@ -585,7 +615,7 @@ static bool conservative_pulse_range(const HostScene& hs, const Shard& sh, int* 
         pmax = std::max(pmax, std::sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]));
         vmin = std::min(vmin, std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]));
     }
-    if (!(pmax > 0) || !(vmin > 0) || !std::isfinite(pmax) || !std::isfinite(vmin)) return false;
+    if (!(pmax > 0) || !(vmin > 0) || !std::isfinite(pmax) || !std::isfinite(vmin)) return B;
     auto fmax = [](const I3B_LUT2d& l) {
         if (!l.have_data) return std::fabs(l.ref_value);
         double m = 0;
@@ -594,23 +624,25 @@ static bool conservative_pulse_range(const HostScene& hs, const Shard& sh, int* 
         return m;
     };
     const double fd = fmax(a.in_geometry.doppler) + fmax(a.out_geometry.doppler);
-    if (!std::isfinite(fd)) return false;
+    if (!std::isfinite(fd)) return B;
     const double wvl = kC / a.fc;
     const double r_max = 1.05 * (og.starting_range + (og.width - 1) * og.range_pixel_spacing);
-    const double cpi = wvl * r_max * (pmax / 6.30e6) / (2.0 * a.ds * vmin);
-    const double shift = 1.2 * fd * wvl * r_max / (2.0 * vmin * vmin);
-    const double t_first = og.sensing_start + sh.line0 / og.prf;
-    const double t_last = og.sensing_start + (sh.line0 + sh.nlines - 1) / og.prf;
-    const double lo = (std::min(t_first, t_last) - 0.5 * cpi - shift - ig.sensing_start) * ig.prf - 64.0;
-    const double hi = (std::max(t_first, t_last) + 0.5 * cpi + shift - ig.sensing_start) * ig.prf + 64.0;
-    if (!std::isfinite(lo) || !std::isfinite(hi)) return false;
-    *k0 = (int) std::max(0.0, std::min(std::floor(lo), (double) ig.length));
-    *k1 = (int) std::max(0.0, std::min(std::ceil(hi), (double) ig.length));
-    return *k1 > *k0;
+    B.cpi = wvl * r_max * (pmax / 6.30e6) / (2.0 * a.ds * vmin);
+    B.shift = 1.2 * fd * wvl * r_max / (2.0 * vmin * vmin);
+    B.t_out0 = og.sensing_start + sh.line0 / og.prf;
+    B.out_prf = og.prf;
+    B.t_in0 = ig.sensing_start;
+    B.in_prf = ig.prf;
+    B.n_pulses = (int) ig.length;
+    B.nlines = sh.nlines;
+    if (!std::isfinite(B.cpi) || !std::isfinite(B.shift)) return B;
+    B.ok = B.upper(sh.nlines) > B.lower(0);
+    return B;
 }
 
 // accumulate pulses [k0, k1) (must be staged) into acc
-static void shard_accumulate(Shard& sh, int k0, int k1, cudaStream_t s)
+static void shard_accumulate(Shard& sh, int k0, int k1, cudaStream_t s, int line_begin = 0,
+                             int line_end = 0, int k_landed = 0)
 {
     AccumParams A = sh.ap;
     A.rc_pitch = sh.rc_pitch;
@@ -618,6 +650,9 @@ static void shard_accumulate(Shard& sh, int k0, int k1, cudaStream_t s)
     A.rc_rows = sh.rc_rows;
     A.k_begin = k0;
     A.k_end = k1;
+    A.line_begin = line_begin;
+    A.line_end = line_end;
+    A.k_landed = k_landed;
     A.tile_mask = nullptr;
     bool done = false;
     if (sh.use_fast) {
@@ -649,10 +684,16 @@ static void shard_accumulate(Shard& sh, int k0, int k1, cudaStream_t s)
     }
 }
 
-// Stage the needed pulses and integrate them, slab by slab: the copy of slab c+1 runs on the
-// copy stream while slab c is integrated on the compute stream.  In the one-shot call the
-// target solve may still be running when this starts (shard_solve_launch): the upload then
-// begins with a conservative pulse range and the solve's result is collected on the way.
+// Stage the needed pulses and integrate them.
+//
+//  * exact pulse range known up front (resident plan, device input, or no host-side bound):
+//    slabs are copied back to back on the copy stream and an accumulation launch is issued
+//    for everything copied so far whenever the compute stream has run dry -- launches end on
+//    absolute multiples of the staged pulse tile, so the image does not depend on the cuts;
+//  * one-shot call from host memory: the upload of a conservative pulse range starts while the
+//    target solve is still running; once the solve is in, whole APERTURES are integrated row
+//    block by row block, each as soon as the pulses its rows can need have landed ("row
+//    wavefront": every tile runs exactly once, over its full pulse range, as in a resident plan).
 static void shard_run(const HostScene& hs, Shard& sh, bool resident_only)
 {
     const I3B_BackprojectArgs& a = hs.a;
@@ -666,13 +707,29 @@ static void shard_run(const HostScene& hs, Shard& sh, bool resident_only)
         const char* e = std::getenv("I3B_NO_EARLY_UPLOAD"); // test / tuning knob
         return e && std::atoi(e) != 0;
     }();
-    int c0 = 0, c1 = 0;
-    bool early = sh.solve_pending && !resident_only && !sh.rc_resident && !devptr && !no_early &&
-                 sh.ap.npix > 0 && conservative_pulse_range(hs, sh, &c0, &c1);
+    // I3B_LAUNCH_PER_SLAB=1 (test knob): one launch per slab, like the reference
+    static const bool per_slab = [] {
+        const char* e = std::getenv("I3B_LAUNCH_PER_SLAB");
+        return e && std::atoi(e) != 0;
+    }();
+    PulseBound bound;
+    if (sh.solve_pending && !resident_only && !sh.rc_resident && !devptr && !no_early && !per_slab && sh.ap.npix > 0)
+        bound = conservative_pulse_bound(hs, sh);
+    bool early = bound.ok;
     if (!early) shard_solve_finish(sh);
     Event ea0, ea1;
     bool ea0_recorded = false;
+    auto mark_start = [&]() {
+        if (!ea0_recorded) {
+            ea0.record(s);
+            ea0_recorded = true;
+        }
+    };
     double ms_h2d = 0.0;
+    const float2* in = reinterpret_cast<const float2*>(a.in);
+    const int slab = std::max(a.batch, 1);
+    std::vector<std::unique_ptr<Event>> landed;
+    std::vector<int> slab_end; // landed[i] fires when pulses < slab_end[i] are on the device
     auto stage_input = [&](int b0, int b1) {
         sh.rc_pitch = (nr + 1) & ~1; // 16-byte line pitch (TMA global stride rule)
         sh.rc_k0 = b0;
@@ -683,7 +740,82 @@ static void shard_run(const HostScene& hs, Shard& sh, bool resident_only)
         // the landed slab (and the pad column) never hold stale bit patterns
         CK(cudaMemsetAsync(sh.rc.p, 0, sh.rc.n * sizeof(float2), sh.copy));
     };
-    if (early || (sh.stats.pulse_last > sh.stats.pulse_first && sh.ap.npix > 0)) {
+    auto upload_slab = [&](int k, int rows) {
+        CK(cudaMemcpy2DAsync(sh.rc.p + (size_t) (k - sh.rc_k0) * sh.rc_pitch,
+                             (size_t) sh.rc_pitch * sizeof(float2), in + (size_t) k * nr,
+                             (size_t) nr * sizeof(float2), (size_t) nr * sizeof(float2), rows,
+                             devptr ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, sh.copy));
+        landed.emplace_back(new Event());
+        landed.back()->record(sh.copy);
+        slab_end.push_back(k + rows);
+        sh.stats.h2d_bytes += (int64_t) rows * nr * (int64_t) sizeof(float2);
+    };
+    const auto t0 = std::chrono::steady_clock::now();
+
+    if (early) {
+        // ---- one-shot call: conservative upload while the solve runs, then row wavefront ----
+        const int b0 = bound.lower(0), b1 = bound.upper(sh.nlines);
+        stage_input(b0, b1);
+        int uploaded = b0, kfirst = 0, klast = 0;
+        bool solved = false, fits = true;
+        size_t n_landed = 0; // slabs known to have landed
+        int rows_done = 0;
+        const int tile_az = sh.ap.tile_az;
+        auto try_launch_rows = [&](bool all_queued) {
+            if (!solved || !fits || klast <= kfirst || rows_done >= sh.nlines) return;
+            while (n_landed < landed.size() && cudaEventQuery(landed[n_landed]->e) == cudaSuccess) ++n_landed;
+            const bool all_landed = all_queued && n_landed == landed.size();
+            // everything needed is queued and either landed or the GPU would otherwise idle:
+            // the last launch takes the rest and waits (in stream order) for the last copy
+            if (all_queued && (all_landed || rows_done > 0)) {
+                mark_start();
+                if (!landed.empty()) CK(cudaStreamWaitEvent(s, landed.back()->e, 0));
+                shard_accumulate(sh, kfirst, klast, s, rows_done, sh.nlines, 0);
+                rows_done = sh.nlines;
+                return;
+            }
+            const int have = n_landed ? slab_end[n_landed - 1] : b0;
+            int r = bound.rows_ready(have);
+            if (r < sh.nlines) r = (r / tile_az) * tile_az;
+            // not worth a launch of its own unless the GPU is idle and a good part is ready
+            if (r - rows_done < std::max(tile_az, sh.nlines / 16)) return;
+            if (rows_done > 0 && cudaStreamQuery(s) != cudaSuccess) return;
+            mark_start();
+            shard_accumulate(sh, kfirst, klast, s, rows_done, r, have);
+            rows_done = r;
+        };
+        while (true) {
+            if (!solved && (uploaded >= b1 || shard_solve_ready(sh))) {
+                shard_solve_finish(sh); // (blocks only when every slab is already queued)
+                solved = true;
+                kfirst = sh.stats.pulse_first;
+                klast = sh.stats.pulse_last;
+                fits = !(klast > kfirst && (kfirst < b0 || klast > b1));
+                if (!fits) break; // the bound did not hold (exotic geometry)
+            }
+            const int stop = solved ? std::max(std::min(klast, b1), b0) : b1;
+            if (uploaded >= stop) break;
+            const int rows = std::min(slab, stop - uploaded);
+            upload_slab(uploaded, rows);
+            uploaded += rows;
+            try_launch_rows(false);
+        }
+        if (fits) {
+            while (klast > kfirst && rows_done < sh.nlines) {
+                try_launch_rows(true);
+                if (rows_done < sh.nlines && n_landed < landed.size())
+                    CK(cudaEventSynchronize(landed[n_landed]->e)); // wait for the next slab
+            }
+        } else {
+            early = false; // fall through to the exact-range path below
+            CK(cudaStreamSynchronize(sh.copy));
+            landed.clear();
+            slab_end.clear();
+        }
+    }
+    if (!early && sh.stats.pulse_last > sh.stats.pulse_first && sh.ap.npix > 0) {
+        // ---- exact pulse range known ----
+        const int kfirst = sh.stats.pulse_first, klast = sh.stats.pulse_last;
         if (!sh.rc_resident && devptr && (nr % 2 == 0)) {
             sh.rc_dev = reinterpret_cast<const float2*>(a.in);
             sh.rc_pitch = nr;
@@ -692,139 +824,38 @@ static void shard_run(const HostScene& hs, Shard& sh, bool resident_only)
             sh.rc_resident = true;
         }
         if (sh.rc_resident) {
-            const int kfirst = sh.stats.pulse_first, klast = sh.stats.pulse_last;
-            ea0.record(s);
-            ea0_recorded = true;
+            mark_start();
             if (!resident_only) shard_accumulate(sh, kfirst, klast, s);
         } else {
-            const float2* in = reinterpret_cast<const float2*>(a.in);
-            const int slab = std::max(a.batch, 1);
-            std::vector<std::unique_ptr<Event>> landed;
-            std::vector<int> slab_end; // landed[i] fires when pulses < slab_end[i] are on the device
-            const auto t0 = std::chrono::steady_clock::now();
-            // I3B_LAUNCH_PER_SLAB=1 (test knob): one launch per slab, like the reference
-            static const bool per_slab = [] {
-                const char* e = std::getenv("I3B_LAUNCH_PER_SLAB");
-                return e && std::atoi(e) != 0;
-            }();
-            int kfirst = 0, klast = 0;   // exact range (known once the solve is in)
-            bool solved = !early;
-            if (solved) {
-                kfirst = sh.stats.pulse_first;
-                klast = sh.stats.pulse_last;
-                stage_input(kfirst, klast);
-            } else {
-                stage_input(c0, c1);
-            }
-            int b0 = sh.rc_k0, b1 = sh.rc_k0 + sh.rc_rows;
-            int pending = kfirst;   // first pulse not yet covered by an accumulation launch
-            int uploaded = b0;      // pulses [b0, uploaded) have been queued for upload
-            bool restart = false;
+            stage_input(kfirst, klast);
             // Slabs are copied back to back; an accumulation launch is issued for everything
             // copied so far whenever the compute stream has run dry (and for the first and the
             // last slab), so a fast host link gives 2 launches per call and a slow one a few
             // more -- not one per slab, each of which would re-run every tile's prologue.
-            bool first_launch = true;
-            while (true) {
-                if (!solved && (uploaded >= b1 || shard_solve_ready(sh))) {
-                    shard_solve_finish(sh); // (blocks only when everything is already queued)
-                    solved = true;
-                    kfirst = sh.stats.pulse_first;
-                    klast = sh.stats.pulse_last;
-                    pending = kfirst;
-                    if (klast > kfirst && (kfirst < b0 || klast > b1)) {
-                        restart = true; // the bound did not hold (exotic geometry): exact range, again
-                        break;
-                    }
-                }
-                const int stop = solved ? std::min(klast, b1) : b1;
-                if (uploaded >= stop) break;
-                const int k = uploaded;
-                const int rows = std::min(slab, stop - k);
-                CK(cudaMemcpy2DAsync(sh.rc.p + (size_t) (k - sh.rc_k0) * sh.rc_pitch,
-                                     (size_t) sh.rc_pitch * sizeof(float2), in + (size_t) k * nr,
-                                     (size_t) nr * sizeof(float2), (size_t) nr * sizeof(float2), rows,
-                                     devptr ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, sh.copy));
-                landed.emplace_back(new Event());
-                landed.back()->record(sh.copy);
-                slab_end.push_back(k + rows);
-                sh.stats.h2d_bytes += (int64_t) rows * nr * (int64_t) sizeof(float2);
-                uploaded = k + rows;
-                if (resident_only || !solved || klast <= kfirst || uploaded <= pending) continue;
-                const bool last = uploaded >= klast;
-                if (first_launch || last || per_slab || cudaStreamQuery(s) == cudaSuccess) {
+            int pending = kfirst; // first pulse not yet covered by an accumulation launch
+            for (int k = kfirst; k < klast; k += slab) {
+                const int rows = std::min(slab, klast - k);
+                upload_slab(k, rows);
+                if (resident_only) continue;
+                const bool first = k == kfirst, last = k + rows >= klast;
+                if (first || last || per_slab || cudaStreamQuery(s) == cudaSuccess) {
                     // launches end on absolute multiples of the staged pulse tile (the last one
                     // at klast): the image is then bit-identical for every batch size and
                     // whatever the host link's timing made of the launch boundaries
-                    const int kend = last ? klast : (uploaded / tk) * tk;
+                    const int kend = last ? klast : ((k + rows) / tk) * tk;
                     if (kend <= pending) continue;
-                    if (!ea0_recorded) {
-                        ea0.record(s);
-                        ea0_recorded = true;
-                    }
+                    mark_start();
                     CK(cudaStreamWaitEvent(s, landed.back()->e, 0));
                     shard_accumulate(sh, pending, kend, s);
                     pending = kend;
-                    first_launch = false;
                 }
             }
-            if (restart) {
-                CK(cudaStreamSynchronize(sh.copy));
-                landed.clear();
-                slab_end.clear();
-                stage_input(kfirst, klast);
-                for (int k = kfirst; k < klast; k += slab) {
-                    const int rows = std::min(slab, klast - k);
-                    CK(cudaMemcpy2DAsync(sh.rc.p + (size_t) (k - sh.rc_k0) * sh.rc_pitch,
-                                         (size_t) sh.rc_pitch * sizeof(float2), in + (size_t) k * nr,
-                                         (size_t) nr * sizeof(float2), (size_t) nr * sizeof(float2), rows,
-                                         cudaMemcpyHostToDevice, sh.copy));
-                    sh.stats.h2d_bytes += (int64_t) rows * nr * (int64_t) sizeof(float2);
-                }
-                landed.emplace_back(new Event());
-                landed.back()->record(sh.copy);
-                slab_end.push_back(klast);
-                pending = kfirst;
-            }
-            // Whatever has not been launched yet (with pinned host memory every slab is queued
-            // long before the solve is in): integrate what has LANDED by now right away, the
-            // rest when its copies are done -- the kernel starts while the upload continues.
-            while (!resident_only && solved && klast > pending) {
-                if (!ea0_recorded) {
-                    ea0.record(s);
-                    ea0_recorded = true;
-                }
-                int kend = klast;
-                Event* wait_for = landed.empty() ? nullptr : landed.back().get();
-                if (!restart && (first_launch || cudaStreamQuery(s) == cudaSuccess)) {
-                    // compute stream is dry: furthest slab that has landed (at least the one
-                    // holding `pending`, which the launch then waits for)
-                    size_t j = 0;
-                    while (j < slab_end.size() && slab_end[j] <= pending) ++j;
-                    size_t best = j;
-                    for (size_t i = j; i < slab_end.size(); ++i) {
-                        if (cudaEventQuery(landed[i]->e) != cudaSuccess) break;
-                        best = i;
-                    }
-                    if (best < slab_end.size() && slab_end[best] < klast) {
-                        const int cut = (slab_end[best] / tk) * tk;
-                        if (cut > pending) {
-                            kend = cut;
-                            wait_for = landed[best].get();
-                        }
-                    }
-                }
-                if (wait_for) CK(cudaStreamWaitEvent(s, wait_for->e, 0));
-                shard_accumulate(sh, pending, kend, s);
-                pending = kend;
-                first_launch = false;
-            }
-            CK(cudaStreamSynchronize(sh.copy));
-            ms_h2d = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
             if (resident_only) sh.rc_resident = true;
         }
     }
-    if (!ea0_recorded) ea0.record(s);
+    if (!sh.rc_resident || resident_only) CK(cudaStreamSynchronize(sh.copy));
+    ms_h2d = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    mark_start();
     ea1.record(s);
     if (resident_only) {
         CK(cudaStreamSynchronize(s));
@@ -841,14 +872,18 @@ static void shard_run(const HostScene& hs, Shard& sh, bool resident_only)
     CK(cudaMemcpyAsync(&st, sh.status.p, sizeof st, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     sh.stats.ms_accumulate = elapsed(ea0, ea1);
-    sh.stats.ms_h2d = ms_h2d;
+    sh.stats.ms_h2d = sh.rc_resident ? 0.0 : ms_h2d;
     sh.stats.used_fast_kernel = sh.use_fast ? 1 : 0;
     sh.stats.fast_variant = sh.use_fast ? sh.fast_variant : -1;
-    if (st.window_overflow && sh.use_fast) {
-        // the staged range window was too small for some gather: redo with the generic kernel
-        sh.use_fast = false;
+    const bool redo_generic = st.window_overflow && sh.use_fast;
+    if (redo_generic || st.premature) {
+        // window_overflow: the staged range window was too small for some gather -> generic
+        // kernel.  premature: a row-wavefront launch met a tile whose pulses had not all landed
+        // (the host-side aperture bound failed) -> everything is on the device by now, again.
+        if (redo_generic) sh.use_fast = false;
         DevStatus clr = st;
         clr.window_overflow = 0;
+        clr.premature = 0;
         CK(cudaMemcpyAsync(sh.status.p, &clr, sizeof clr, cudaMemcpyHostToDevice, s));
         CK(cudaMemsetAsync(sh.acc.p, 0, sh.acc.n * sizeof(double2), s));
         Event eb0, eb1;
@@ -858,7 +893,7 @@ static void shard_run(const HostScene& hs, Shard& sh, bool resident_only)
         launch_finalize(sh.ap.npix, sh.ap.out_width, sh.pix.p, sh.acc.p, sh.out.p, sh.range_cor_view, hs.a.mantissa_nbits, s);
         CK(cudaStreamSynchronize(s));
         sh.stats.ms_accumulate += elapsed(eb0, eb1);
-        sh.stats.used_fast_kernel = 0;
+        if (redo_generic) sh.stats.used_fast_kernel = 0;
     }
 }
 

@@ -97,7 +97,7 @@ struct DevStatus {
     int hard_error;  // I3B_EXC_* (orbit domain error under border mode Error)
     int window_overflow; // fast kernel: a gather fell outside its staged tile
     int kmin, kmax;      // pulse span [kmin, kmax) needed by the solved pixels
-    int pad;
+    int premature;       // a row-wavefront launch met a tile whose pulses had not all landed
     unsigned long long pixel_pulses; // sum (kstop - kstart)
 };
 

@@ -44,6 +44,13 @@ struct AccumParams {
     // is flagged bad (tiles holding failed pixels are skipped by the fast kernel)
     const TileInfo* tile_mask;
     int tile_az, tile_rg, tiles_rg;
+    // output lines [line_begin, line_end) of the shard are processed by this launch
+    // (line_end == 0: all); line_begin is a multiple of tile_az
+    int line_begin, line_end;
+    // pulses < k_landed are on the device (row-wavefront launches of the one-shot call, which
+    // integrate whole apertures of the rows whose pulses have landed): a tile that needs more
+    // sets DevStatus::premature and is left alone.  0: everything in [k_begin, k_end) is there.
+    int k_landed;
 };
 
 void launch_pulse_table(const DevOrbit& orbit, Linspace in_time, double fc, PulseRec* pulse,
