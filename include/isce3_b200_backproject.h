@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define I3B_ABI_VERSION 2
+#define I3B_ABI_VERSION 3
 
 /* ---- status codes --------------------------------------------------------
  * 0..11 mirror isce3::error::ErrorCode (cxx/isce3/error/ErrorCode.h:8-21): they
@@ -220,6 +220,21 @@ typedef struct {
                                 significant ones like truncate_mantissa(z, n)
                                 (python/packages/isce3/core/types.py:116-171)          */
     int32_t _pad2;
+
+    /* non-uniform pulse timing extension (ABI 3).  The reference API can only describe
+     * uniformly spaced pulses (RadarGeometry::sensingTime() is a Linspace,
+     * container/RadarGeometry.icc:28-42), so the workflow first RESAMPLES dithered-PRF raw
+     * data onto a uniform grid (nisar/workflows/focus.py:973-1061) -- a full pass over the
+     * swath that time-domain backprojection does not need: it only wants to know where the
+     * platform was at each pulse.
+     *   pulse_times: azimuth time (s since the reference epoch) of every input line
+     *   [in_geometry.grid.length], strictly increasing; NULL: the uniform grid
+     *   sensing_start + k / prf.  The platform state of pulse k is the input orbit at
+     *   pulse_times[k]; a pixel integrates the pulses from the last one at or before the start
+     *   of its coherent processing interval up to (not including) the first one at or after
+     *   its end -- for uniform times exactly the floor / ceil of Backproject.cpp:186-193.
+     *   in_geometry.grid.prf stays the nominal PRF.                                       */
+    const double* pulse_times;
 } I3B_BackprojectArgs;
 
 enum {

@@ -15,7 +15,7 @@ from pathlib import Path
 
 import numpy as np
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # status codes (include/isce3_b200_backproject.h)
 SUCCESS = 0
@@ -170,6 +170,7 @@ class BackprojectArgs(C.Structure):
         ("range_cor", C.c_void_p),
         ("mantissa_nbits", C.c_int32),
         ("_pad2", C.c_int32),
+        ("pulse_times", C.c_void_p),
     ]
 
 

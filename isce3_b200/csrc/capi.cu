@@ -242,6 +242,7 @@ struct HostScene {
     I3B_BackprojectArgs a;
     std::vector<double> out_pos, out_vel, in_pos, in_vel, out_dop, in_dop;
     std::vector<float> dem, kdata, range_cor;
+    std::vector<double> pulse_times; // padded: [-kPulsePadLo, n + kPulsePadHi), empty: uniform grid
     std::vector<int> devices;
 };
 
@@ -282,6 +283,13 @@ static void validate(const I3B_BackprojectArgs& a)
         if (a.dem.method == I3B_INTERP_SINC) bad("sinc DEM interpolation is not supported");
     }
     if (!(a.fc > 0) || !(a.ds > 0)) bad("fc and ds must be positive");
+    if (a.pulse_times) {
+        const int64_t n = ig.grid.length;
+        for (int64_t k = 0; k < n; ++k) {
+            if (!std::isfinite(a.pulse_times[k])) bad("pulse_times must be finite");
+            if (k > 0 && !(a.pulse_times[k] > a.pulse_times[k - 1])) bad("pulse_times must be strictly increasing");
+        }
+    }
     if (a.mantissa_nbits < 0 || a.mantissa_nbits > 23) bad("mantissa_nbits must be in [0, 23]");
     const I3B_Kernel& k = a.kernel;
     switch (k.kind) {
@@ -355,7 +363,7 @@ struct Shard {
     } streams;
     cudaStream_t& compute = streams.compute;
     cudaStream_t& copy = streams.copy;
-    DevBuf<double> out_pos, out_vel, in_pos, in_vel, out_dop, in_dop, pv;
+    DevBuf<double> out_pos, out_vel, in_pos, in_vel, out_dop, in_dop, pv, times;
     DevBuf<float> dem, kdata, height;
     DevBuf<PulseRec> pulse;
     DevBuf<PixelRec> pix;
@@ -449,6 +457,11 @@ static void shard_setup(const HostScene& hs, Shard& sh)
     P.out_time = Linspace {og.grid.sensing_start, 1.0 / og.grid.prf, (int) og.grid.length};
     P.out_range = Linspace {og.grid.starting_range, og.grid.range_pixel_spacing, (int) og.grid.width};
     P.in_time = Linspace {ig.grid.sensing_start, 1.0 / ig.grid.prf, (int) ig.grid.length};
+    P.in_times = nullptr;
+    if (!hs.pulse_times.empty()) {
+        sh.times.upload(hs.pulse_times.data(), hs.pulse_times.size(), s);
+        P.in_times = sh.times.p + kPulsePadLo;
+    }
     P.out_orbit = dev_orbit(og.orbit, sh.out_pos.p, sh.out_vel.p);
     P.in_orbit = dev_orbit(ig.orbit, sh.in_pos.p, sh.in_vel.p);
     P.out_doppler = dev_lut(og.doppler, sh.out_dop.p);
@@ -502,6 +515,10 @@ static void shard_setup(const HostScene& hs, Shard& sh)
     char why[160] = "";
     I3B_TapPolyFit fit;
     sh.use_fast = !(a.flags & I3B_FLAG_FORCE_GENERIC) && fast_fit(sh.host_kernel, &fit, why, sizeof why);
+    // The fast kernel models the carrier phase as a cubic in the pulse INDEX between exact
+    // evaluations 64 pulses apart; with jittered pulse times the phase is smooth in time, not in
+    // index, so non-uniform pulse trains take the generic kernel (exact geometry per pulse).
+    if (!hs.pulse_times.empty()) sh.use_fast = false;
     sh.fast_variant = sh.use_fast ? fit.imm_variant : -1;
     std::memset(&sh.stats, 0, sizeof sh.stats);
     sh.stats.taps = A.kernel.taps;
@@ -526,7 +543,7 @@ static void shard_solve_launch(const HostScene& hs, Shard& sh)
     CK(cudaMemcpyAsync(sh.status.p, &init, sizeof init, cudaMemcpyHostToDevice, s));
     sh.ev_solve0->record(s);
     if (!sh.pulse_shared) {
-        launch_pulse_table(sh.sp.in_orbit, sh.sp.in_time, hs.a.fc, sh.pulse.p + kPulsePadLo, sh.pv.p, sh.status.p, s);
+        launch_pulse_table(sh.sp.in_orbit, sh.sp.in_time, sh.sp.in_times, hs.a.fc, sh.pulse.p + kPulsePadLo, sh.pv.p, sh.status.p, s);
         CK(cudaGetLastError());
     }
     launch_target_solve(sh.sp, sh.pix.p, sh.height.p, sh.tile_info.p, (int) sh.tile_info.n, sh.status.p, s);
@@ -713,7 +730,8 @@ static void shard_run(const HostScene& hs, Shard& sh, bool resident_only)
         return e && std::atoi(e) != 0;
     }();
     PulseBound bound;
-    if (sh.solve_pending && !resident_only && !sh.rc_resident && !devptr && !no_early && !per_slab && sh.ap.npix > 0)
+    if (sh.solve_pending && !resident_only && !sh.rc_resident && !devptr && !no_early && !per_slab &&
+        sh.ap.npix > 0 && hs.pulse_times.empty())
         bound = conservative_pulse_bound(hs, sh);
     bool early = bound.ok;
     if (!early) shard_solve_finish(sh);
@@ -751,6 +769,11 @@ static void shard_run(const HostScene& hs, Shard& sh, bool resident_only)
         sh.stats.h2d_bytes += (int64_t) rows * nr * (int64_t) sizeof(float2);
     };
     const auto t0 = std::chrono::steady_clock::now();
+    static const bool debug_timing = std::getenv("I3B_DEBUG_TIMING") != nullptr;
+    auto since = [&]() {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    };
+    double t_solved = 0, t_first = -1, t_queued = 0;
 
     if (early) {
         // ---- one-shot call: conservative upload while the solve runs, then row wavefront ----
@@ -770,6 +793,7 @@ static void shard_run(const HostScene& hs, Shard& sh, bool resident_only)
             if (all_queued && (all_landed || rows_done > 0)) {
                 mark_start();
                 if (!landed.empty()) CK(cudaStreamWaitEvent(s, landed.back()->e, 0));
+                if (t_first < 0) t_first = since();
                 shard_accumulate(sh, kfirst, klast, s, rows_done, sh.nlines, 0);
                 rows_done = sh.nlines;
                 return;
@@ -777,10 +801,11 @@ static void shard_run(const HostScene& hs, Shard& sh, bool resident_only)
             const int have = n_landed ? slab_end[n_landed - 1] : b0;
             int r = bound.rows_ready(have);
             if (r < sh.nlines) r = (r / tile_az) * tile_az;
-            // not worth a launch of its own unless the GPU is idle and a good part is ready
+            // a launch of its own only for a good part of the block (at most ~16 launches; with
+            // a slow host link they queue up behind each other and the GPU never idles)
             if (r - rows_done < std::max(tile_az, sh.nlines / 16)) return;
-            if (rows_done > 0 && cudaStreamQuery(s) != cudaSuccess) return;
             mark_start();
+            if (t_first < 0) t_first = since();
             shard_accumulate(sh, kfirst, klast, s, rows_done, r, have);
             rows_done = r;
         };
@@ -788,6 +813,7 @@ static void shard_run(const HostScene& hs, Shard& sh, bool resident_only)
             if (!solved && (uploaded >= b1 || shard_solve_ready(sh))) {
                 shard_solve_finish(sh); // (blocks only when every slab is already queued)
                 solved = true;
+                t_solved = since();
                 kfirst = sh.stats.pulse_first;
                 klast = sh.stats.pulse_last;
                 fits = !(klast > kfirst && (kfirst < b0 || klast > b1));
@@ -853,6 +879,7 @@ static void shard_run(const HostScene& hs, Shard& sh, bool resident_only)
             if (resident_only) sh.rc_resident = true;
         }
     }
+    t_queued = since();
     if (!sh.rc_resident || resident_only) CK(cudaStreamSynchronize(sh.copy));
     ms_h2d = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     mark_start();
@@ -873,6 +900,11 @@ static void shard_run(const HostScene& hs, Shard& sh, bool resident_only)
     CK(cudaStreamSynchronize(s));
     sh.stats.ms_accumulate = elapsed(ea0, ea1);
     sh.stats.ms_h2d = sh.rc_resident ? 0.0 : ms_h2d;
+    if (debug_timing && early)
+        fprintf(stderr, "[i3b]   run: solve in at %.1f, first launch %.1f, all queued %.1f, copies done %.1f, "
+                        "synced %.1f ms; launches %d; solve kernel %.1f, accumulate %.1f ms\n",
+                t_solved, t_first, t_queued, ms_h2d, since(), sh.stats.accumulate_launches,
+                sh.stats.ms_target_solve, sh.stats.ms_accumulate);
     sh.stats.used_fast_kernel = sh.use_fast ? 1 : 0;
     sh.stats.fast_variant = sh.use_fast ? sh.fast_variant : -1;
     const bool redo_generic = st.window_overflow && sh.use_fast;
@@ -946,6 +978,25 @@ static std::unique_ptr<I3B_Plan> make_plan(const I3B_BackprojectArgs* args, bool
             hs.a.range_cor = hs.range_cor.data();
         }
     }
+    if (args->pulse_times && args->in_geometry.grid.length > 0) {
+        // explicit pulse times that ARE the uniform grid take the uniform path (bit-identical to
+        // a call without them); otherwise keep a copy extended past both ends with the first /
+        // last pulse interval (the pulse table is padded, see kPulsePadLo / kPulsePadHi)
+        const I3B_RadarGrid& g = args->in_geometry.grid;
+        const int64_t n = g.length;
+        const double dt = 1.0 / g.prf;
+        bool uniform = true;
+        for (int64_t k = 0; k < n && uniform; ++k) uniform = args->pulse_times[k] == g.sensing_start + (double) k * dt;
+        if (!uniform) {
+            const double* T = args->pulse_times;
+            const double d0 = n > 1 ? T[1] - T[0] : dt, d1 = n > 1 ? T[n - 1] - T[n - 2] : dt;
+            hs.pulse_times.resize((size_t) n + kPulsePadLo + kPulsePadHi);
+            for (int64_t k = -kPulsePadLo; k < n + kPulsePadHi; ++k)
+                hs.pulse_times[(size_t) (k + kPulsePadLo)] =
+                        k < 0 ? T[0] + (double) k * d0 : (k >= n ? T[n - 1] + (double) (k - n + 1) * d1 : T[k]);
+        }
+    }
+    hs.a.pulse_times = nullptr; // (the scene's own copy is the one used from here on)
     int ndev_avail = 0;
     {
         cudaError_t e = cudaGetDeviceCount(&ndev_avail);
@@ -1177,7 +1228,7 @@ static void scene_setup(const HostScene& hs, Shard& sc)
     init.kmin = INT_MAX;
     init.kmax = INT_MIN;
     CK(cudaMemcpyAsync(sc.status.p, &init, sizeof init, cudaMemcpyHostToDevice, s));
-    launch_pulse_table(sc.sp.in_orbit, sc.sp.in_time, a.fc, sc.pulse.p + kPulsePadLo, sc.pv.p, sc.status.p, s);
+    launch_pulse_table(sc.sp.in_orbit, sc.sp.in_time, sc.sp.in_times, a.fc, sc.pulse.p + kPulsePadLo, sc.pv.p, sc.status.p, s);
     CK(cudaGetLastError());
     DevStatus st;
     CK(cudaMemcpyAsync(&st, sc.status.p, sizeof st, cudaMemcpyDeviceToHost, s));

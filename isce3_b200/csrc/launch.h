@@ -15,6 +15,9 @@ struct TileInfo {
 
 struct SolveParams {
     Linspace out_time, out_range, in_time;
+    // explicit pulse times (non-uniform PRF): device array indexed like the pulse table, from
+    // -kPulsePadLo to n_pulses + kPulsePadHi (extrapolated past both ends); null: in_time
+    const double* in_times;
     DevOrbit out_orbit, in_orbit;
     DevLUT2d out_doppler, in_doppler;
     DevDEM dem;
@@ -53,8 +56,8 @@ struct AccumParams {
     int k_landed;
 };
 
-void launch_pulse_table(const DevOrbit& orbit, Linspace in_time, double fc, PulseRec* pulse,
-                        double* pv, DevStatus* status, cudaStream_t s);
+void launch_pulse_table(const DevOrbit& orbit, Linspace in_time, const double* in_times, double fc,
+                        PulseRec* pulse, double* pv, DevStatus* status, cudaStream_t s);
 void launch_target_solve(const SolveParams& P, PixelRec* pix, float* height, TileInfo* tiles,
                          int n_tiles, DevStatus* status, cudaStream_t s);
 void launch_accumulate_generic(const AccumParams& P, const PixelRec* pix, const double* pv,

@@ -12,8 +12,8 @@ namespace i3b {
 
 // ---- per-pulse table ---------------------------------------------------------
 // Replaces the host loop Backproject.cpp:101-106 (orbit border mode Error).
-__global__ void pulse_table_kernel(DevOrbit orbit, Linspace in_time, double fc, PulseRec* pulse,
-                                   double* pv, DevStatus* status)
+__global__ void pulse_table_kernel(DevOrbit orbit, Linspace in_time, const double* __restrict__ in_times,
+                                   double fc, PulseRec* pulse, double* pv, DevStatus* status)
 {
     // pulse[] is indexed from -kPulsePadLo (the pointer passed in is already offset)
     const int k = (int) (blockIdx.x * blockDim.x + threadIdx.x) - kPulsePadLo;
@@ -22,7 +22,8 @@ __global__ void pulse_table_kernel(DevOrbit orbit, Linspace in_time, double fc, 
     D3 p, v;
     // pulses of the input grid: border mode Error like Backproject.cpp:101-106; padding
     // entries: smooth orbit extrapolation (never contributes to a pixel)
-    const int st = orbit_interpolate(orbit, in_time[k], in_grid ? BORDER_ERROR : BORDER_EXTRAPOLATE, &p, &v);
+    const double tk = in_times ? in_times[k] : in_time[k];
+    const int st = orbit_interpolate(orbit, tk, in_grid ? BORDER_ERROR : BORDER_EXTRAPOLATE, &p, &v);
     if (st != I3B_SUCCESS) {
         if (in_grid) status->hard_error = I3B_EXC_OUT_OF_RANGE;
         p = v = nan3();
@@ -112,6 +113,26 @@ target_solve_kernel(SolveParams P, PixelRec* __restrict__ pix, float* __restrict
                 const double t0 = P.in_time.first, dt = P.in_time.spacing;
                 kstart = (int) floor((tstart - t0) / dt);
                 kstop = (int) ceil((tstop - t0) / dt);
+                if (P.in_times) {
+                    // explicit pulse times: last pulse at or before tstart, first pulse at or
+                    // after tstop (what floor / ceil select on a uniform grid); binary searches
+                    const double* T = P.in_times;
+                    const int n = P.in_time.size;
+                    int lo = 0, hi = n; // upper_bound(tstart)
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if (T[mid] <= tstart) lo = mid + 1;
+                        else hi = mid;
+                    }
+                    kstart = lo - 1;
+                    lo = 0, hi = n; // lower_bound(tstop)
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if (T[mid] < tstop) lo = mid + 1;
+                        else hi = mid;
+                    }
+                    kstop = lo;
+                }
                 kstart = max(kstart, 0);
                 kstop = min(kstop, P.in_time.size);
                 double tau_atm = 0.;
@@ -320,11 +341,11 @@ void launch_geo2rdr_batch(const DevOrbit& orbit, const DevLUT2d& dop, double wvl
 
 // ---- launchers -------------------------------------------------------------------------
 
-void launch_pulse_table(const DevOrbit& orbit, Linspace in_time, double fc, PulseRec* pulse,
-                        double* pv, DevStatus* status, cudaStream_t s)
+void launch_pulse_table(const DevOrbit& orbit, Linspace in_time, const double* in_times, double fc,
+                        PulseRec* pulse, double* pv, DevStatus* status, cudaStream_t s)
 {
     const int n = in_time.size + kPulsePadLo + kPulsePadHi;
-    pulse_table_kernel<<<(n + 127) / 128, 128, 0, s>>>(orbit, in_time, fc, pulse, pv, status);
+    pulse_table_kernel<<<(n + 127) / 128, 128, 0, s>>>(orbit, in_time, in_times, fc, pulse, pv, status);
 }
 
 void launch_target_solve(const SolveParams& P, PixelRec* pix, float* height, TileInfo* tiles,

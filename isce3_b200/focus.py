@@ -113,7 +113,7 @@ def _check_array(a, name, dtype, shape, what):
 def build_args(out, out_geometry, in_, in_geometry, dem, fc, ds, kernel,
                dry_tropo_model="tsx", rdr2geo_params=None, geo2rdr_params=None, batch=1024,
                height=None, devices=None, force_generic=False, range_cor=None,
-               mantissa_nbits=None) -> Flattened:
+               mantissa_nbits=None, pulse_times=None) -> Flattened:
     """Validate like the reference binding and flatten into an I3B_BackprojectArgs."""
     oshape = (out_geometry.grid_length, out_geometry.grid_width)
     ishape = (in_geometry.grid_length, in_geometry.grid_width)
@@ -164,6 +164,11 @@ def build_args(out, out_geometry, in_, in_geometry, dem, fc, ds, kernel,
         if not 0 < int(mantissa_nbits) <= 23:  # isce3/core/types.py:147-151
             raise InvalidArgument(f"Require 0 < significant_bits={mantissa_nbits} <= 23")
         a.mantissa_nbits = int(mantissa_nbits) % 23  # 23 keeps every bit
+    if pulse_times is not None:
+        pt = fl.hold(pulse_times, np.float64)
+        if pt.shape != (ishape[0],):
+            raise InvalidArgument("pulse_times length must match the number of input lines")
+        a.pulse_times = pt.ctypes.data
     if devices:
         dev = np.ascontiguousarray(devices, dtype=np.int32)
         fl.keep.append(dev)
@@ -197,7 +202,7 @@ def last_stats() -> dict:
 def backproject(out, out_geometry, in_, in_geometry, dem, fc, ds, kernel,
                 dry_tropo_model="tsx", rdr2geo_params=None, geo2rdr_params=None, batch=1024,
                 height=None, *, devices=None, force_generic=False, range_cor=None,
-                mantissa_nbits=None) -> bool:
+                mantissa_nbits=None, pulse_times=None) -> bool:
     """Focus in azimuth via time-domain backprojection on B200.
 
     Same positional arguments, defaults and return value as
@@ -207,11 +212,14 @@ def backproject(out, out_geometry, in_, in_geometry, dem, fc, ds, kernel,
     (complex64 per output range column) and ``mantissa_nbits`` (keyword-only extensions) fuse
     what the workflow's writer does to each block on the host -- ``z *= range_cor`` and
     ``truncate_mantissa(z, n)`` (nisar/workflows/focus.py:899-925) -- into the device pass
-    that produces ``out``.
+    that produces ``out``.  ``pulse_times`` (keyword-only extension): azimuth time of every
+    input line for non-uniformly spaced pulses (dithered PRF) -- focuses them where they were
+    recorded instead of resampling the raw data to a uniform grid first
+    (nisar/workflows/focus.py:973-1061).
     """
     fl = build_args(out, out_geometry, in_, in_geometry, dem, fc, ds, kernel, dry_tropo_model,
                     rdr2geo_params, geo2rdr_params, batch, height, devices, force_generic,
-                    range_cor, mantissa_nbits)
+                    range_cor, mantissa_nbits, pulse_times)
     if out is None:
         raise TypeError("output array is required")
     lib = _capi.load_library()
@@ -229,12 +237,12 @@ class BackprojectPlan:
 
     def __init__(self, out_geometry, in_, in_geometry, dem, fc, ds, kernel,
                  dry_tropo_model="tsx", rdr2geo_params=None, geo2rdr_params=None, batch=1024,
-                 force_generic=False, devices=None):
+                 force_generic=False, devices=None, pulse_times=None):
         self._lib = _capi.load_library()
         self._shape = (out_geometry.grid_length, out_geometry.grid_width)
         fl = build_args(None, out_geometry, in_, in_geometry, dem, fc, ds, kernel,
                         dry_tropo_model, rdr2geo_params, geo2rdr_params, batch, None, devices,
-                        force_generic)
+                        force_generic, pulse_times=pulse_times)
         self._handle = C.c_void_p()
         status = self._lib.i3b_plan_create(C.byref(fl.args), C.byref(self._handle))
         if status < 0:
@@ -287,11 +295,11 @@ class BlockFocuser:
 
     def __init__(self, out_geometry, in_, in_geometry, dem, fc, ds, kernel, dry_tropo_model="tsx",
                  rdr2geo_params=None, geo2rdr_params=None, devices=None, force_generic=False,
-                 range_cor=None, mantissa_nbits=None):
+                 range_cor=None, mantissa_nbits=None, pulse_times=None):
         self._lib = _capi.load_library()
         self._fl = build_args(None, out_geometry, in_, in_geometry, dem, fc, ds, kernel, dry_tropo_model,
                               rdr2geo_params, geo2rdr_params, 1024, None, devices, force_generic,
-                              range_cor, mantissa_nbits)
+                              range_cor, mantissa_nbits, pulse_times)
         self._handle = C.c_void_p()
         status = self._lib.i3b_blocks_create(C.byref(self._fl.args), C.byref(self._handle))
         if status < 0:

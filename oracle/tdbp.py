@@ -83,9 +83,14 @@ class Oracle:
     # -- whole path -----------------------------------------------------------
     def backproject(self, out, out_geometry, in_, in_geometry, dem, fc, ds, kernel,
                     dry_tropo_model="tsx", rdr2geo_params=None, geo2rdr_params=None,
-                    height=None, return_status=False):
+                    height=None, return_status=False, pulse_times=None):
+        """``pulse_times`` (explicit, possibly non-uniform azimuth time of every input line; an
+        extension the reference API cannot express) is honoured by the restated port only."""
+        if pulse_times is not None and "port" not in self.kind:
+            raise RuntimeError("pulse_times needs the restated port oracle (tdbp.port())")
         fl = build_args(out, out_geometry, in_, in_geometry, dem, fc, ds, kernel,
-                        dry_tropo_model, rdr2geo_params, geo2rdr_params, 1024, height)
+                        dry_tropo_model, rdr2geo_params, geo2rdr_params, 1024, height,
+                        pulse_times=pulse_times)
         status = self._backproject(C.byref(fl.args))
         if status < 0:
             raise RuntimeError(f"oracle[{self.kind}] status {status}: "

@@ -560,8 +560,10 @@ static int backproject(const I3B_BackprojectArgs& a, double* pp_out)
 
     // :101-106 platform position & velocity at each pulse (border mode Error)
     std::vector<V3> pos(in_lines), vel(in_lines);
+    // (ABI 3 extension, not in the reference: explicit pulse times; see the header)
+    const double* T = a.pulse_times;
     for (int i = 0; i < in_lines; ++i) {
-        const double t = in_t0 + i * in_dt;
+        const double t = T ? T[i] : in_t0 + i * in_dt;
         if (orbit_interpolate(ig.orbit, t, BORDER_ERROR, &pos[i], &vel[i]) != I3B_SUCCESS) {
             g_err = "orbit interpolation outside of orbit domain";
             return I3B_EXC_OUT_OF_RANGE;
@@ -623,6 +625,12 @@ static int backproject(const I3B_BackprojectArgs& a, double* pp_out)
             const double tstart = t - 0.5 * cpi, tstop = t + 0.5 * cpi;
             int kstart = (int) std::floor((tstart - in_t0) / in_dt); // :190-193
             int kstop = (int) std::ceil((tstop - in_t0) / in_dt);
+            if (T) {
+                // last pulse at or before tstart / first pulse at or after tstop: what floor and
+                // ceil above select on a uniform grid
+                kstart = (int) (std::upper_bound(T, T + in_lines, tstart) - T) - 1;
+                kstop = (int) (std::lower_bound(T, T + in_lines, tstop) - T);
+            }
             kstart = std::max(kstart, 0);
             kstop = std::min(kstop, in_lines);
             double tau_atm = 0.; // :196-199

@@ -200,6 +200,7 @@ class Scene:
     range_sample_rate: float
     rdr2geo_params: dict = dataclasses.field(default_factory=dict)
     geo2rdr_params: dict = dataclasses.field(default_factory=dict)
+    pulse_times: object = None  # float64 [pulses] when the pulse train is non-uniform
 
     def backproject_args(self):
         """Positional arguments 2..9 of backproject (after `out`)."""
@@ -212,10 +213,13 @@ class Scene:
 
 
 def simulate_echoes(rc, in_grid: RadarGridParameters, orbit: Orbit, targets, fc, bandwidth, fs,
-                    tau_atm=None, halfwidth=48, pulse_window=None):
-    """Add point-target echoes into rc (complex64 [pulses, bins]) in place."""
+                    tau_atm=None, halfwidth=48, pulse_window=None, pulse_times=None):
+    """Add point-target echoes into rc (complex64 [pulses, bins]) in place.  ``pulse_times``:
+    explicit (non-uniform) azimuth time of every pulse; default the uniform grid of ``in_grid``."""
     npulse, nr = rc.shape
     tk = in_grid.sensing_start + np.arange(npulse) / in_grid.prf
+    if pulse_times is not None:
+        tk = np.asarray(pulse_times, dtype=np.float64)
     pos, vel = interpolate_orbit_many(orbit, tk)
     tau0 = 2.0 * in_grid.starting_range / C0
     dtau = 2.0 * in_grid.range_pixel_spacing / C0
@@ -322,10 +326,14 @@ def make_scene(name="c1", *, pulses=None, bins=None, out_lines=None, out_samples
                n_targets=None, noise_db=None, taps=None, seed=1234, dry_tropo_model=None,
                with_dem=None, ds=None, table_size=2048, doppler_lut=False,
                look_side=LookSide.Left, out_range_spacing_ratio=1.0, out_prf_ratio=1.0,
-               dem_epsg=None):
+               dem_epsg=None, prf_dither=0.0):
     """Build one of the named synthetic configurations (see module docstring).
     ``dem_epsg``: CRS of the raster DEM (configurations with relief): None / 4326, "utm" (the
-    zone of the scene centre) or an EPSG code createProj knows (3031, 3413, 6933, 326xx...)."""
+    zone of the scene centre) or an EPSG code createProj knows (3031, 3413, 6933, 326xx...).
+    ``prf_dither``: > 0 makes the pulse train NON-uniform -- pulse k is transmitted at
+    ``t0 + (k + d_k) / prf`` with d_k a fixed slow pattern of that amplitude (in pulse
+    intervals) plus a small pulse-to-pulse jitter, like a dithered-PRF acquisition;
+    the times are returned in ``Scene.pulse_times`` and the echoes are simulated there."""
     base = name.lower()
     airborne = base.startswith("c5")
     fc = 1.2575e9
@@ -426,11 +434,20 @@ def make_scene(name="c1", *, pulses=None, bins=None, out_lines=None, out_samples
             if cfg["tropo"] == "tsx":
                 p, _ = orbit.interpolate(tt)
                 tau_atm.append(dry_tropo_delay_tsx(p, ecef_to_llh(xyz)))
+    pulse_times = None
+    if prf_dither > 0:
+        k = np.arange(npulse)
+        # slow PRF stepping (offsets of up to `prf_dither` pulse intervals accumulate and
+        # unwind over 97 pulses) plus a small pulse-to-pulse jitter; stays strictly increasing
+        jit = np.random.default_rng(seed + 7).uniform(-0.5, 0.5, npulse)
+        pulse_times = t_first + (k + prf_dither * np.sin(2 * np.pi * k / 97.0) +
+                                 0.1 * min(prf_dither, 1.0) * jit) / prf
+        assert np.all(np.diff(pulse_times) > 0)
     rc = np.zeros((npulse, nbins), np.complex64)
     simulate_echoes(rc, in_grid, orbit, targets, fc, bw, fs,
-                    tau_atm=np.array(tau_atm) if tau_atm else None)
+                    tau_atm=np.array(tau_atm) if tau_atm else None, pulse_times=pulse_times)
     if cfg["noise_db"] is not None:
         add_noise(rc, 10.0 ** (cfg["noise_db"] / 20.0), seed)
     kernel = knab_table_kernel(cfg["taps"], bw / fs if not airborne else 0.8, table_size)
     return Scene(name, in_geom, out_geom, rc, dem, fc, float(cfg["ds"]), kernel, cfg["tropo"],
-                 targets, bw, fs)
+                 targets, bw, fs, pulse_times=pulse_times)

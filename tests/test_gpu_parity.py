@@ -717,3 +717,51 @@ def test_blocks_api_equals_per_block_calls(oracle):
     want = np.zeros((10, 100), np.complex64)
     backproject(want, sc.out_subgrid(8, 18, 150, 250), *common[1:], range_cor=cor[150:250])
     np.testing.assert_array_equal(o, want)
+
+
+def test_non_uniform_pulse_times(oracles):
+    """ABI 3 extension ``pulse_times`` (dithered PRF without the resampling pre-pass of
+    nisar/workflows/focus.py:973-1061).  Pinned three ways: (i) explicit times that ARE the
+    uniform grid give the bit-identical image of a call without them; (ii) on a dithered pulse
+    train the GPU equals the restated port oracle run with the same times (the reference API
+    cannot express them); (iii) physics: the point target focuses at its pixel with gain =
+    #pulses and the IRF of the uniform acquisition, while ignoring the times defocuses it."""
+    port, _ = oracles
+    kw = dict(pulses=4096, bins=1024, out_lines=40, out_samples=72, n_targets=1, noise_db=False)
+    uni = synth.make_scene("c2", **kw)
+    g = uni.in_geometry.radar_grid
+    t_uniform = g.sensing_start + np.arange(g.length) / g.prf
+    plain = run_gpu(uni)
+    same = run_gpu(uni, pulse_times=t_uniform)
+    np.testing.assert_array_equal(same[1], plain[1])
+    assert same[3]["used_fast_kernel"] == 1
+
+    dit = synth.make_scene("c2", prf_dither=2.0, **kw)
+    assert np.max(np.abs(dit.pulse_times - t_uniform)) * g.prf > 1.5
+    gpu = run_gpu(dit, pulse_times=dit.pulse_times)
+    ref = np.zeros(shape_of(dit), np.complex64)
+    href = np.zeros(shape_of(dit), np.float32)
+    err = port.backproject(ref, *dit.backproject_args(), height=href, pulse_times=dit.pulse_times)
+    check(gpu, (err, ref, href), dit)
+    tg = dit.targets[0]
+    i, j = int(tg.az_index), int(tg.rg_index)
+    n_int = gpu[3]["pixel_pulses"] / ref.size
+    assert np.unravel_index(np.argmax(np.abs(gpu[1])), ref.shape) == (i, j)
+    assert abs(abs(gpu[1][i, j]) - n_int) < 0.02 * n_int
+    ignored = run_gpu(dit)  # same echoes, pulse times not given: defocused
+    assert abs(ignored[1][i, j]) < 0.6 * abs(gpu[1][i, j])
+    r = np.asarray(dit.out_geometry.slant_range)
+    carrier = np.exp(-1j * 4 * np.pi / (core.speed_of_light / dit.fc) * r)[None, :]
+    a, _ = point_target.analyze_point_target(gpu[1] * carrier, i, j, nov=32, chipsize=32)
+    b, _ = point_target.analyze_point_target(plain[1] * carrier, i, j, nov=32, chipsize=32)
+    for axis in ("azimuth", "range"):
+        assert abs(a[axis]["offset"] - b[axis]["offset"]) <= 0.01
+        assert abs(a[axis]["resolution"] - b[axis]["resolution"]) <= 0.02 * b[axis]["resolution"]
+    # argument checks
+    out = np.zeros(shape_of(dit), np.complex64)
+    with pytest.raises(focus.InvalidArgument):
+        backproject(out, *dit.backproject_args(), pulse_times=dit.pulse_times[:-1])
+    bad = dit.pulse_times.copy()
+    bad[100] = bad[99]
+    with pytest.raises(focus.InvalidArgument, match="strictly increasing"):
+        backproject(out, *dit.backproject_args(), pulse_times=bad)
