@@ -782,32 +782,54 @@ static void shard_run(const HostScene& hs, Shard& sh, bool resident_only)
         int uploaded = b0, kfirst = 0, klast = 0;
         bool solved = false, fits = true;
         size_t n_landed = 0; // slabs known to have landed
-        int rows_done = 0;
+        int rows_done = 0;   // rows [0, rows_done) have been handed their whole apertures
+        int k_split = 0;     // rows >= rows_done have been integrated over pulses < k_split
+        bool split_set = false;
         const int tile_az = sh.ap.tile_az;
+        // Launch policy once the solve is in.  Rows whose every pulse has landed get their whole
+        // remaining aperture in one launch (row wavefront); while no row block is ready and the
+        // GPU would idle -- the first rows need a full aperture on the device, most of the upload
+        // when the block is short -- the landed pulses are integrated for ALL remaining rows
+        // (pulse split, on a pulse-tile boundary).  Either way each pixel sees its pulses in
+        // order, whole pulse tiles at a time: the image does not depend on the cuts.
         auto try_launch_rows = [&](bool all_queued) {
             if (!solved || !fits || klast <= kfirst || rows_done >= sh.nlines) return;
+            if (!split_set) {
+                k_split = kfirst;
+                split_set = true;
+            }
             while (n_landed < landed.size() && cudaEventQuery(landed[n_landed]->e) == cudaSuccess) ++n_landed;
             const bool all_landed = all_queued && n_landed == landed.size();
-            // everything needed is queued and either landed or the GPU would otherwise idle:
-            // the last launch takes the rest and waits (in stream order) for the last copy
+            // everything needed is queued and either landed or a launch is already running: the
+            // last launch takes the rest and waits (in stream order) for the last copy
             if (all_queued && (all_landed || rows_done > 0)) {
                 mark_start();
                 if (!landed.empty()) CK(cudaStreamWaitEvent(s, landed.back()->e, 0));
                 if (t_first < 0) t_first = since();
-                shard_accumulate(sh, kfirst, klast, s, rows_done, sh.nlines, 0);
+                shard_accumulate(sh, k_split, klast, s, rows_done, sh.nlines, 0);
                 rows_done = sh.nlines;
                 return;
             }
             const int have = n_landed ? slab_end[n_landed - 1] : b0;
             int r = bound.rows_ready(have);
             if (r < sh.nlines) r = (r / tile_az) * tile_az;
-            // a launch of its own only for a good part of the block (at most ~16 launches; with
-            // a slow host link they queue up behind each other and the GPU never idles)
-            if (r - rows_done < std::max(tile_az, sh.nlines / 16)) return;
-            mark_start();
-            if (t_first < 0) t_first = since();
-            shard_accumulate(sh, kfirst, klast, s, rows_done, r, have);
-            rows_done = r;
+            // a launch of its own only for a good part of the block (with a slow host link the
+            // launches queue up behind each other and the GPU never idles)
+            if (r - rows_done >= std::max(tile_az, sh.nlines / 32)) {
+                mark_start();
+                if (t_first < 0) t_first = since();
+                shard_accumulate(sh, k_split, klast, s, rows_done, r, have);
+                rows_done = r;
+                return;
+            }
+            // nothing row-ready: keep an idle GPU busy with the pulses that have landed
+            const int k1 = std::min((have / tk) * tk, klast);
+            if (k1 - k_split >= 8 * tk && (t_first < 0 || cudaStreamQuery(s) == cudaSuccess)) {
+                mark_start();
+                if (t_first < 0) t_first = since();
+                shard_accumulate(sh, k_split, k1, s, rows_done, sh.nlines, 0);
+                k_split = k1;
+            }
         };
         while (true) {
             if (!solved && (uploaded >= b1 || shard_solve_ready(sh))) {

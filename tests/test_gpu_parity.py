@@ -765,3 +765,30 @@ def test_non_uniform_pulse_times(oracles):
     bad[100] = bad[99]
     with pytest.raises(focus.InvalidArgument, match="strictly increasing"):
         backproject(out, *dit.backproject_args(), pulse_times=bad)
+
+
+def test_compiled_pybind11_binding_gives_the_same_image(oracle):
+    """isce3_b200.ext._backproject -- the compiled binding with the reference's call shape
+    (pybind_isce3/cuda/focus/Backproject.cpp:25-117) -- against the ctypes route and the oracle,
+    raster DEM / Doppler LUT / Chebyshev kernel included; geometry failures come back as True."""
+    import isce3_b200.ext.isce3 as isce
+    for kw in (dict(name="c2", pulses=2048, bins=1024, out_lines=12, out_samples=150, n_targets=1),
+               dict(name="c4", pulses=1024, bins=1024, out_lines=10, out_samples=130, n_targets=1,
+                    doppler_lut=True)):
+        kw = dict(kw)
+        sc = synth.make_scene(kw.pop("name"), **kw)
+        direct = run_gpu(sc)
+        out = np.zeros(shape_of(sc), np.complex64)
+        h = np.zeros(shape_of(sc), np.float32)
+        err = isce.cuda.focus.backproject(out, *sc.backproject_args(), height=h)
+        assert err is direct[0]
+        np.testing.assert_array_equal(out, direct[1])
+        np.testing.assert_array_equal(h, direct[2])
+    sc.kernel = core.ChebyKernelF32(core.KnabKernel(9.0, 0.8), 16)
+    direct = run_gpu(sc)
+    isce.cuda.focus.backproject(out, *sc.backproject_args())
+    np.testing.assert_array_equal(out, direct[1])
+    check((direct[0], out, direct[2], direct[3]), run_cpu(oracle, sc), sc)
+    sc.rdr2geo_params = {"look_min": 0.0, "look_max": 0.3}
+    assert isce.cuda.focus.backproject(out, *sc.backproject_args()) is True
+    assert np.isnan(out).all()
