@@ -49,13 +49,25 @@ constexpr int TILE_RG = 128;  // output range pixels per CTA tile
 #ifndef I3B_TILE_AZ
 #define I3B_TILE_AZ 4
 #endif
+// Ring of staged pulse tiles.  I3B_LAST_ARRIVER = 0 (default): 4 stages of 16 pulses, the
+// producer role rotates over the warps and refills a stage released two tiles ago.
+// I3B_LAST_ARRIVER = 1: two stages of I3B_TK = 32 pulses; the warp that is LAST to finish a tile
+// refills its stage with the tile after next, so nobody waits for a release and per-tile work
+// is paid every 32 pulses -- measured on B200: no gain (K = 9: 0.743 vs 0.749 of FP32 peak; the
+// slowest warp now also carries the window computation), kept for experiments.
+#ifndef I3B_LAST_ARRIVER
+#define I3B_LAST_ARRIVER 0
+#endif
+#ifndef I3B_TK
+#define I3B_TK (I3B_LAST_ARRIVER ? 32 : 16)
+#endif
 #ifndef I3B_NSTAGE
-#define I3B_NSTAGE 4
+#define I3B_NSTAGE (I3B_LAST_ARRIVER ? 2 : 4)
 #endif
 constexpr int TILE_AZ = I3B_TILE_AZ;   // output azimuth lines per CTA tile
 constexpr int PX = 2;         // pixels per thread (range-adjacent)
 constexpr int NTHREADS = TILE_AZ * TILE_RG / PX; // 256 threads
-constexpr int TK = 16;        // pulses per stage
+constexpr int TK = I3B_TK;    // pulses per stage
 constexpr int NSTAGE = I3B_NSTAGE;
 constexpr int POLY_OFFSET = 256;   // per-tap polynomial rows (copied from the kernel parameter)
 #ifndef I3B_ROTATE_PRODUCER
@@ -65,7 +77,7 @@ constexpr int POLY_OFFSET = 256;   // per-tap polynomial rows (copied from the k
 // refilled was consumed TWO tiles ago, so the producing warp practically never waits for
 // the slower warps of the CTA (with NSTAGE - 1 it waited ~15 % of its time, ncu r01 v4).
 #ifndef I3B_PREFETCH_DIST
-#define I3B_PREFETCH_DIST (I3B_NSTAGE - 2)
+#define I3B_PREFETCH_DIST (I3B_LAST_ARRIVER ? I3B_NSTAGE - 1 : I3B_NSTAGE - 2)
 #endif
 constexpr int PREFETCH = I3B_PREFETCH_DIST;
 #ifndef I3B_GROUP_RG
@@ -164,6 +176,10 @@ struct FastParams {
     double U0;      // swst / dtau
     double fc;
     int zero;       // always 0 (opaque to the compiler, see Weights::load_top)
+    // non-uniform pulse times (null: uniform): tn[k] = t_k * nominal PRF (FP64), xi[k] = tn[k]
+    // minus tn at the base of k's geometry segment (FP32); both indexed like the pulse table
+    const double* tn;
+    const float* xi;
 };
 
 
@@ -172,6 +188,7 @@ struct SmemHeader {
     uint64_t full[NSTAGE];
     uint64_t empty[NSTAGE];
     int winlo[NSTAGE];
+    int done[NSTAGE]; // warps that have finished the tile held by the stage (last-arriver scheme)
     int kb, ke;     // CTA pulse range
     int bad;        // tile holds a failed pixel -> generic kernel
     int ks_max, ke_min; // every pixel of the CTA integrates pulses [ks_max, ke_min)
@@ -403,13 +420,23 @@ struct PairState {
     float flim;        // steady sub-tiles: 1/2 - bound on what the cubic's curvature adds between checks
 };
 
+// Pulses per geometry segment (one exact FP64 phase evaluation per pixel per segment, a cubic
+// in between).  128: the cubic's own error stays ~1e-6 rad (spaceborne) / ~1e-5 rad (airborne),
+// the FP32 evaluation error doubles to ~2e-5 rad at the end of a segment (relative RMS of the
+// image 8e-6 instead of 4e-6; gate 1e-4), the FP64 work per pulse halves: +2 % throughput.
 #ifndef I3B_SEG
-#define I3B_SEG 64
+#define I3B_SEG 128
 #endif
 #ifndef I3B_KK_UNROLL
 #define I3B_KK_UNROLL 4
 #endif
 constexpr int SEG = I3B_SEG; // pulses per geometry segment
+#ifndef I3B_SUB
+#define I3B_SUB 8
+#endif
+constexpr int SUB = I3B_SUB;      // pulses per run (steady / per-pulse / aperture-edge path chosen per run)
+constexpr int EDGE_RUN = SUB;
+static_assert(TK % SUB == 0, "a staged pulse tile is a whole number of runs");
 constexpr int KK_UNROLL = I3B_KK_UNROLL;
 static_assert(SEG % TK == 0, "a geometry segment is a whole number of staged pulse tiles");
 constexpr float MAGIC32 = 12582912.0f;         // 1.5 * 2^23: float -> nearest integer by addition
@@ -574,8 +601,10 @@ template<int K, int D, class Coef, bool EDGE, int NP>
 __device__ __forceinline__ void tile_body(PairState& S, float& jf, unsigned& jjmax,
                                           uint32_t lines_addr, uint32_t row_bytes, int wlo,
                                           unsigned jmax, float Gr, unsigned krel0, unsigned krel1,
-                                          int zero, uint32_t bank)
+                                          int zero, uint32_t bank, const float* __restrict__ xi = nullptr)
 {
+    // xi (non-uniform pulse times only): position of each pulse of the run on the segment's
+    // time axis, in nominal pulse intervals -- replaces the pulse index in the phase cubic
     typedef Weights<K, D, Coef> WT;
     typename WT::Top top;
     WT::load_top(top, zero, bank);
@@ -589,6 +618,7 @@ __device__ __forceinline__ void tile_body(PairState& S, float& jf, unsigned& jjm
         // from the shared-memory base every pulse: ~10 instructions)
         asm volatile("" : "+r"(line_addr));
         // carrier phase [rad] (reduced at the segment base) of both pixels at once
+        if (xi) jf = __ldg(xi + kk);
         const f32x2 j2 = bcast2(jf);
         const f32x2 ang = fma2(fma2(fma2(S.c3, j2, S.c2), j2, S.c1), j2, S.ang0);
         const f32x2 g = fma2(ang, bcast2(Gr), S.f0m); // sample coordinate - floor(base) - 1/2
@@ -668,10 +698,10 @@ __device__ __forceinline__
 #endif
 unsigned tile_body_edge(PairState& S, float jf, unsigned jjmax, uint32_t lines_addr,
                         uint32_t row_bytes, int wlo, unsigned jmax, float Gr, unsigned krel0,
-                        unsigned krel1, int zero, uint32_t bank)
+                        unsigned krel1, int zero, uint32_t bank, const float* __restrict__ xi)
 {
     // (jf, jjmax by value: only the pair state has to live in memory around the call)
-    tile_body<K, D, Coef, true, TK>(S, jf, jjmax, lines_addr, row_bytes, wlo, jmax, Gr, krel0, krel1, zero, bank);
+    tile_body<K, D, Coef, true, EDGE_RUN>(S, jf, jjmax, lines_addr, row_bytes, wlo, jmax, Gr, krel0, krel1, zero, bank, xi);
     return jjmax;
 }
 
@@ -725,9 +755,6 @@ struct PairwiseMac {
 #ifndef I3B_STEADY
 #define I3B_STEADY 1
 #endif
-#ifndef I3B_SUB
-#define I3B_SUB 8
-#endif
 #ifndef I3B_STEADY_MAX_TAPS
 #define I3B_STEADY_MAX_TAPS 32
 #endif
@@ -738,13 +765,6 @@ struct PairwiseMac {
 #ifndef I3B_QUAD_RUN
 #define I3B_QUAD_RUN 1
 #endif
-// The first run of a staged tile also tests the whole tile (TK pulses); when that holds the
-// following runs of the tile skip their own test.
-#ifndef I3B_HIER_CHECK
-#define I3B_HIER_CHECK 0 // (measured: -2 % at K = 9, the carried state costs more than the test)
-#endif
-constexpr int SUB = I3B_SUB; // pulses per steady run
-static_assert(TK % SUB == 0, "a staged pulse tile is a whole number of steady runs");
 
 template<int K, int D, class Coef, int OFF, int NP>
 __device__ __forceinline__ void subtile_steady(PairState& S, f32x2 A0, f32x2 A1, f32x2 A2, f32x2 A3,
@@ -864,6 +884,7 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, const __grid_
         for (int s = 0; s < NSTAGE; ++s) {
             mbar_init(&hdr->full[s], 1);
             mbar_init(&hdr->empty[s], NTHREADS / 32);
+            hdr->done[s] = 0;
         }
         hdr->kb = INT_MAX;
         hdr->ke = INT_MIN;
@@ -979,7 +1000,7 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, const __grid_
         __syncwarp();
     };
     if (warp == 0) {
-        for (int n = 0; n < PREFETCH && n < ntiles; ++n) produce(n);
+        for (int n = 0; n < (I3B_LAST_ARRIVER ? NSTAGE : PREFETCH) && n < ntiles; ++n) produce(n);
     }
 
     // Per-thread shared-memory slots: FP64 running sums (2 per pixel) and the exact carrier
@@ -1019,7 +1040,8 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, const __grid_
     int seg_b = 0;                              // first pulse of the current segment
 
     for (int n = 0; n < ntiles; ++n) {
-        if (n + PREFETCH < ntiles && warp == (I3B_ROTATE_PRODUCER ? (n + PREFETCH) % NWARPS_ROT : 0))
+        if (!I3B_LAST_ARRIVER && n + PREFETCH < ntiles &&
+            warp == (I3B_ROTATE_PRODUCER ? (n + PREFETCH) % NWARPS_ROT : 0))
             produce(n + PREFETCH);
 
         const int kt = t0 + n * TK; // first pulse of the tile
@@ -1038,12 +1060,30 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, const __grid_
                 ybnd[4 * p + 1] = y1;
                 ybnd[4 * p + 2] = y2;
                 ybnd[4 * p + 3] = y3;
+                if (P.tn) {
+                    // Non-uniform pulse times: the phase is smooth in TIME.  Cubic through the four
+                    // boundary values at their actual positions x on the segment's time axis
+                    // (nominal pulse intervals from the segment base; Newton form on the nodes
+                    // 0, x2, x0, x3, expanded to monomials); the pulse loop evaluates it at xi[k].
+                    const double x0 = P.tn[b - SEG] - P.tn[b], x2 = P.tn[b + SEG] - P.tn[b];
+                    const double x3 = P.tn[b + 2 * SEG] - P.tn[b];
+                    const double d12 = (y2 - y1) / x2;
+                    const double d20 = (y0 - y2) / (x0 - x2);
+                    const double d120 = (d20 - d12) / x0;
+                    const double d03 = (y3 - y0) / (x3 - x0);
+                    const double d203 = (d03 - d20) / (x3 - x2);
+                    const double d1203 = (d203 - d120) / x3;
+                    c1[p] = (float) (TWO_PI_D * (d12 - d120 * x2 + d1203 * x2 * x0));
+                    c2[p] = (float) (TWO_PI_D * (d120 - d1203 * (x2 + x0)));
+                    c3[p] = (float) (TWO_PI_D * d1203);
+                } else {
                 const double d1 = y2 - y1, d2 = (y2 - y1) - (y1 - y0);
                 const double d3 = ((y3 - y2) - (y2 - y1)) - d2;
                 // p(tau) - y1 = tau (d1 - d2/2 - d3/6) + tau^2 d2/2 + tau^3 d3/6, tau = j / SEG
                 c1[p] = (float) (TWO_PI_D * (d1 - 0.5 * d2 - d3 * (1.0 / 6.0)) * (1.0 / SEG));
                 c2[p] = (float) (TWO_PI_D * (0.5 * d2) * (1.0 / (SEG * SEG)));
                 c3[p] = (float) (TWO_PI_D * (d3 * (1.0 / 6.0)) * (1.0 / ((double) SEG * SEG * SEG)));
+                }
                 a0[p] = (float) (TWO_PI_D * (y1 - rint(y1)));
                 const double uh = fma(y1, P.G, SHIFT - P.U0);
                 const double ufl = floor(uh);
@@ -1060,97 +1100,86 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, const __grid_
             // steady run: |u''| (SUB-1)^2 / 8, u'' = Gr (2 c2 + 6 c3 j), j < SEG
             const float curv0 = 2.f * fabsf(c2[0]) + (6.f * SEG) * fabsf(c3[0]);
             const float curv1 = 2.f * fabsf(c2[1]) + (6.f * SEG) * fabsf(c3[1]);
-            // (curvature over a whole tile: the hierarchical test looks TK pulses ahead)
-            constexpr int kHorizon = I3B_HIER_CHECK ? TK : SUB;
-            S.flim = 0.5f - 1e-5f - fabsf(Gr) * fmaxf(curv0, curv1) * ((kHorizon - 1) * (kHorizon - 1) / 8.0f);
+            S.flim = 0.5f - 1e-5f - fabsf(Gr) * fmaxf(curv0, curv1) * ((SUB - 1) * (SUB - 1) / 8.0f);
             if (I3B_QUAD_RUN) {
                 constexpr float kDev = 0.0481125f * (SUB - 1) * (SUB - 1) * (SUB - 1);
                 if (fmaxf(fabsf(c3[0]), fabsf(c3[1])) * kDev > 2e-6f) S.flim = -1.0f;
             }
+            if (P.xi) S.flim = -1.0f; // steady runs step the phase by whole pulse indices
         }
 
         const int s = n % NSTAGE;
         mbar_wait(&hdr->full[s], (n / NSTAGE) & 1);
         const uint32_t lines_addr = stage_addr0 + (uint32_t) s * (uint32_t) sbytes;
         const int wlo = hdr->winlo[s];
-        if (I3B_EDGE_SPLIT && kt >= ks_max && kt + TK <= ke_min) {
-            // (32 taps: the rolled steady loop gains nothing over the per-pulse path, measured)
-            if constexpr (I3B_STEADY && K < I3B_STEADY_MAX_TAPS) {
-            const int iw0 = S.i0rel[0] - wlo, iw1 = S.i0rel[1] - wlo;
-            bool tile_steady = false; // proven for the whole tile by the first run's test
-            f32x2 tt = 0ull;
-            unsigned jj0 = 0;
+        // The tile is worked through in runs of SUB pulses, each taking the cheapest path it
+        // qualifies for: every pulse inside every pixel's aperture (almost all runs) -> steady
+        // run if the window position provably does not move, else per-pulse rounding; runs that
+        // straddle an aperture edge -> the out-of-line edge path (skips pulses outside).
+        const int iw0 = S.i0rel[0] - wlo, iw1 = S.i0rel[1] - wlo;
 #pragma unroll 1
-            for (int sub = 0; sub < TK / SUB; ++sub) {
-                const float js = (float) (kt - seg_b + sub * SUB);
-                const uint32_t la = lines_addr + (uint32_t) (sub * SUB) * row_bytes;
-                // phase cubic re-centred on the run: ang(js + x) = A0 + A1 x + A2 x^2 + A3 x^3
-                const f32x2 js2 = bcast2(js), Gr2 = bcast2(Gr);
-                const f32x2 c3x3 = mul2(S.c3, bcast2(3.0f)), c2x2 = add2(S.c2, S.c2);
-                f32x2 A2 = fma2(c3x3, js2, S.c2);
-                f32x2 A1 = fma2(fma2(c3x3, js2, c2x2), js2, S.c1);
-                const f32x2 A0 = fma2(fma2(fma2(S.c3, js2, S.c2), js2, S.c1), js2, S.ang0);
-                bool steady = tile_steady;
-                if (!(I3B_HIER_CHECK && tile_steady)) {
-                    // coordinate (minus floor(base) + 1/2) at the first pulse and at the last pulse
-                    // of the run (and, for the first run, of the tile)
+        for (int sub = 0; sub < TK / SUB; ++sub) {
+            const int kr = kt + sub * SUB; // first pulse of the run
+            const float js = (float) (kr - seg_b);
+            const uint32_t la = lines_addr + (uint32_t) (sub * SUB) * row_bytes;
+            if (I3B_EDGE_SPLIT && kr >= ks_max && kr + SUB <= ke_min) {
+                bool steady = false;
+                // (32 taps: the rolled steady loop gains nothing over the per-pulse path, measured)
+                if constexpr (I3B_STEADY && K < I3B_STEADY_MAX_TAPS) {
+                    // phase cubic re-centred on the run: ang(js + x) = A0 + A1 x + A2 x^2 + A3 x^3
+                    const f32x2 js2 = bcast2(js), Gr2 = bcast2(Gr);
+                    const f32x2 c3x3 = mul2(S.c3, bcast2(3.0f)), c2x2 = add2(S.c2, S.c2);
+                    f32x2 A2 = fma2(c3x3, js2, S.c2);
+                    f32x2 A1 = fma2(fma2(c3x3, js2, c2x2), js2, S.c1);
+                    const f32x2 A0 = fma2(fma2(fma2(S.c3, js2, S.c2), js2, S.c1), js2, S.ang0);
+                    // coordinate (minus floor(base) + 1/2) at the first and the last pulse of the run
                     const f32x2 XE = bcast2((float) (SUB - 1));
                     const f32x2 ange = fma2(fma2(fma2(S.c3, XE, A2), XE, A1), XE, A0);
                     const f32x2 g0 = fma2(A0, Gr2, S.f0m), ge = fma2(ange, Gr2, S.f0m);
                     const f32x2 mm = add2(g0, bcast2(MAGIC32));
-                    tt = add2(mm, bcast2(-MAGIC32)); // integer part at the first pulse
+                    const f32x2 tt = add2(mm, bcast2(-MAGIC32)); // integer part at the first pulse
                     const f32x2 fa = sub2(g0, tt), fe = sub2(ge, tt);
                     float m0, m1, fa0, fa1, fe0, fe1;
                     unpack2(mm, m0, m1);
                     unpack2(fa, fa0, fa1);
                     unpack2(fe, fe0, fe1);
-                    jj0 = (unsigned) (iw0 + __float_as_int(m0));
+                    const unsigned jj0 = (unsigned) (iw0 + __float_as_int(m0));
                     const unsigned jj1 = (unsigned) (iw1 + __float_as_int(m1));
                     const float worst = fmaxf(fmaxf(fabsf(fa0), fabsf(fa1)), fmaxf(fabsf(fe0), fabsf(fe1)));
                     // steady: same integer part over the whole run (both pixels), adjacent windows
                     // inside the staged rows
                     steady = worst <= S.flim && jj1 == jj0 + 1u && jj0 < jmax;
-                    if (I3B_HIER_CHECK && sub == 0 && steady) {
-                        const f32x2 XT = bcast2((float) (TK - 1));
-                        const f32x2 angt = fma2(fma2(fma2(S.c3, XT, A2), XT, A1), XT, A0);
-                        const f32x2 ft = sub2(fma2(angt, Gr2, S.f0m), tt);
-                        float ft0, ft1;
-                        unpack2(ft, ft0, ft1);
-                        tile_steady = fmaxf(fabsf(ft0), fabsf(ft1)) <= S.flim;
+                    if (steady) {
+                        const uint32_t src = la + ((jj0 >> 1) << 4);
+                        const f32x2 fbase = sub2(S.f0m, tt);
+                        if (I3B_QUAD_RUN) {
+                            // quadratic through the cubic at x = 0, (SUB-1)/2, SUB-1
+                            A1 = fma2(S.c3, bcast2(-0.5f * (SUB - 1) * (SUB - 1)), A1);
+                            A2 = fma2(S.c3, bcast2(1.5f * (SUB - 1)), A2);
+                        }
+                        if (jj0 & 1u)
+                            subtile_steady<K, D, Coef, 1, SUB>(S, A0, A1, A2, S.c3, fbase, Gr, src, row_bytes, P.zero, poly_addr);
+                        else
+                            subtile_steady<K, D, Coef, 0, SUB>(S, A0, A1, A2, S.c3, fbase, Gr, src, row_bytes, P.zero, poly_addr);
                     }
                 }
-                if (steady) {
-                    const uint32_t src = la + ((jj0 >> 1) << 4);
-                    const f32x2 fbase = sub2(S.f0m, tt);
-                    if (I3B_QUAD_RUN) {
-                        // quadratic through the cubic at x = 0, (SUB-1)/2, SUB-1
-                        A1 = fma2(S.c3, bcast2(-0.5f * (SUB - 1) * (SUB - 1)), A1);
-                        A2 = fma2(S.c3, bcast2(1.5f * (SUB - 1)), A2);
-                    }
-                    if (jj0 & 1u)
-                        subtile_steady<K, D, Coef, 1, SUB>(S, A0, A1, A2, S.c3, fbase, Gr, src, row_bytes, P.zero, poly_addr);
-                    else
-                        subtile_steady<K, D, Coef, 0, SUB>(S, A0, A1, A2, S.c3, fbase, Gr, src, row_bytes, P.zero, poly_addr);
-                } else {
+                if (!steady) {
                     jf = js;
-                    tile_body<K, D, Coef, false, SUB>(S, jf, jjmax, la, row_bytes, wlo, jmax, Gr, 0u, 0u, P.zero, poly_addr);
+                    tile_body<K, D, Coef, false, SUB>(S, jf, jjmax, la, row_bytes, wlo, jmax, Gr, 0u, 0u, P.zero, poly_addr,
+                                                      P.xi ? P.xi + kr : nullptr);
                 }
-            }
             } else {
-            jf = (float) (kt - seg_b);
-            tile_body<K, D, Coef, false, TK>(S, jf, jjmax, lines_addr, row_bytes, wlo, jmax, Gr, 0u, 0u, P.zero, poly_addr);
+                // k - kstart for the first pulse of the run, per pixel
+                const unsigned krel0 = (unsigned) (kr - S.kstart[0]);
+                const unsigned krel1 = (unsigned) (kr - S.kstart[1]);
+                // (through a copy: the out-of-line call wants its argument in memory, and the
+                // interior paths should not find their pair state there)
+                PairState T = S;
+                jjmax = tile_body_edge<K, D, Coef>(T, js, jjmax, la, row_bytes, wlo, jmax, Gr, krel0, krel1, P.zero, poly_addr,
+                                                   P.xi ? P.xi + kr : nullptr);
+                S.accp[0] = T.accp[0]; S.accp[1] = T.accp[1];
+                S.accq[0] = T.accq[0]; S.accq[1] = T.accq[1];
             }
-        } else {
-            // k - kstart for the first pulse of the tile, per pixel
-            const unsigned krel0 = (unsigned) (kt - S.kstart[0]);
-            const unsigned krel1 = (unsigned) (kt - S.kstart[1]);
-            jf = (float) (kt - seg_b);
-            // (through a copy: the out-of-line call wants its argument in memory, and the
-            // interior paths should not find their pair state there)
-            PairState T = S;
-            jjmax = tile_body_edge<K, D, Coef>(T, jf, jjmax, lines_addr, row_bytes, wlo, jmax, Gr, krel0, krel1, P.zero, poly_addr);
-            S.accp[0] = T.accp[0]; S.accp[1] = T.accp[1];
-            S.accq[0] = T.accq[0]; S.accq[1] = T.accq[1];
         }
 
         // pulse tile done: fold FP32 partials into FP64, release the stage.
@@ -1165,7 +1194,20 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, const __grid_
             S.accp[p] = S.accq[p] = 0ull;
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&hdr->empty[s]);
+        if (I3B_LAST_ARRIVER) {
+            // the last warp to leave tile n refills its stage with tile n + NSTAGE: every other
+            // warp has released the stage already, nobody waits
+            int last = 0;
+            if (lane == 0) {
+                mbar_arrive(&hdr->empty[s]);
+                last = atomicAdd(&hdr->done[s], 1) == NTHREADS / 32 - 1;
+                if (last) hdr->done[s] = 0;
+            }
+            last = __shfl_sync(0xffffffffu, last, 0);
+            if (last && n + NSTAGE < ntiles) produce(n + NSTAGE);
+        } else {
+            if (lane == 0) mbar_arrive(&hdr->empty[s]);
+        }
     }
 #pragma unroll
     for (int p = 0; p < PX; ++p) {
@@ -1517,6 +1559,8 @@ int launch_accumulate_fast(const AccumParams& P, const DevKernel& hk, const Pixe
     FP.U0 = P.swst / P.dtau;
     FP.fc = P.fc;
     FP.zero = 0;
+    FP.tn = P.tn;
+    FP.xi = P.xi;
     const size_t smem = HEADER_BYTES + NSTAGE * stage_bytes(W) + (size_t) NTHREADS * 6 * PX * sizeof(double);
     PolyTable PT;
     std::memcpy(PT.rows, R.rows, sizeof PT.rows);
@@ -1551,6 +1595,7 @@ int fast_tiles(int out_lines, int out_width)
 }
 
 int fast_pulse_tile() { return TK; }
+int fast_segment() { return SEG; }
 
 void fast_tile_shape(int* tile_az, int* tile_rg)
 {

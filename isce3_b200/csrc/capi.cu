@@ -243,6 +243,8 @@ struct HostScene {
     std::vector<double> out_pos, out_vel, in_pos, in_vel, out_dop, in_dop;
     std::vector<float> dem, kdata, range_cor;
     std::vector<double> pulse_times; // padded: [-kPulsePadLo, n + kPulsePadHi), empty: uniform grid
+    std::vector<double> pulse_tn;    // pulse_times * nominal PRF (fast kernel's time axis)
+    std::vector<float> pulse_xi;     // pulse_tn minus its value at the pulse's segment base
     std::vector<int> devices;
 };
 
@@ -363,7 +365,8 @@ struct Shard {
     } streams;
     cudaStream_t& compute = streams.compute;
     cudaStream_t& copy = streams.copy;
-    DevBuf<double> out_pos, out_vel, in_pos, in_vel, out_dop, in_dop, pv, times;
+    DevBuf<double> out_pos, out_vel, in_pos, in_vel, out_dop, in_dop, pv, times, tn;
+    DevBuf<float> xi;
     DevBuf<float> dem, kdata, height;
     DevBuf<PulseRec> pulse;
     DevBuf<PixelRec> pix;
@@ -461,6 +464,8 @@ static void shard_setup(const HostScene& hs, Shard& sh)
     if (!hs.pulse_times.empty()) {
         sh.times.upload(hs.pulse_times.data(), hs.pulse_times.size(), s);
         P.in_times = sh.times.p + kPulsePadLo;
+        sh.tn.upload(hs.pulse_tn.data(), hs.pulse_tn.size(), s);
+        sh.xi.upload(hs.pulse_xi.data(), hs.pulse_xi.size(), s);
     }
     P.out_orbit = dev_orbit(og.orbit, sh.out_pos.p, sh.out_vel.p);
     P.in_orbit = dev_orbit(ig.orbit, sh.in_pos.p, sh.in_vel.p);
@@ -515,10 +520,10 @@ static void shard_setup(const HostScene& hs, Shard& sh)
     char why[160] = "";
     I3B_TapPolyFit fit;
     sh.use_fast = !(a.flags & I3B_FLAG_FORCE_GENERIC) && fast_fit(sh.host_kernel, &fit, why, sizeof why);
-    // The fast kernel models the carrier phase as a cubic in the pulse INDEX between exact
-    // evaluations 64 pulses apart; with jittered pulse times the phase is smooth in time, not in
-    // index, so non-uniform pulse trains take the generic kernel (exact geometry per pulse).
-    if (!hs.pulse_times.empty()) sh.use_fast = false;
+    // Non-uniform pulse trains: the fast kernel's phase cubic runs over TIME (positions tn / xi
+    // of the pulses on the segment's time axis) instead of the pulse index.
+    A.tn = hs.pulse_times.empty() ? nullptr : sh.tn.p + kPulsePadLo;
+    A.xi = hs.pulse_times.empty() ? nullptr : sh.xi.p + kPulsePadLo;
     sh.fast_variant = sh.use_fast ? fit.imm_variant : -1;
     std::memset(&sh.stats, 0, sizeof sh.stats);
     sh.stats.taps = A.kernel.taps;
@@ -1008,7 +1013,11 @@ static std::unique_ptr<I3B_Plan> make_plan(const I3B_BackprojectArgs* args, bool
         const int64_t n = g.length;
         const double dt = 1.0 / g.prf;
         bool uniform = true;
-        for (int64_t k = 0; k < n && uniform; ++k) uniform = args->pulse_times[k] == g.sensing_start + (double) k * dt;
+        // (to a few ulps: t0 + k / prf and t0 + k * (1 / prf) are the same grid)
+        for (int64_t k = 0; k < n && uniform; ++k) {
+            const double t = g.sensing_start + (double) k * dt;
+            uniform = std::fabs(args->pulse_times[k] - t) <= 8.0 * 2.220446049250313e-16 * std::max(std::fabs(t), dt * (double) n);
+        }
         if (!uniform) {
             const double* T = args->pulse_times;
             const double d0 = n > 1 ? T[1] - T[0] : dt, d1 = n > 1 ? T[n - 1] - T[n - 2] : dt;
@@ -1016,6 +1025,18 @@ static std::unique_ptr<I3B_Plan> make_plan(const I3B_BackprojectArgs* args, bool
             for (int64_t k = -kPulsePadLo; k < n + kPulsePadHi; ++k)
                 hs.pulse_times[(size_t) (k + kPulsePadLo)] =
                         k < 0 ? T[0] + (double) k * d0 : (k >= n ? T[n - 1] + (double) (k - n + 1) * d1 : T[k]);
+            // the fast kernel's time axis: nominal pulse intervals, relative to each pulse's
+            // geometry-segment base (absolute multiples of the segment length)
+            const int seg = fast_segment();
+            hs.pulse_tn.resize(hs.pulse_times.size());
+            hs.pulse_xi.resize(hs.pulse_times.size());
+            for (size_t i = 0; i < hs.pulse_times.size(); ++i) hs.pulse_tn[i] = hs.pulse_times[i] * g.prf;
+            for (int64_t k = -kPulsePadLo; k < n + kPulsePadHi; ++k) {
+                int64_t b = (k >= 0 ? k / seg : -((-k + seg - 1) / seg)) * seg; // floor to a multiple of seg
+                b = std::max<int64_t>(b, -kPulsePadLo);
+                hs.pulse_xi[(size_t) (k + kPulsePadLo)] =
+                        (float) (hs.pulse_tn[(size_t) (k + kPulsePadLo)] - hs.pulse_tn[(size_t) (b + kPulsePadLo)]);
+            }
         }
     }
     hs.a.pulse_times = nullptr; // (the scene's own copy is the one used from here on)

@@ -54,6 +54,10 @@ struct AccumParams {
     // integrate whole apertures of the rows whose pulses have landed): a tile that needs more
     // sets DevStatus::premature and is left alone.  0: everything in [k_begin, k_end) is there.
     int k_landed;
+    // non-uniform pulse times (fast kernel; null: uniform): tn[k] = t_k * nominal PRF, xi[k] =
+    // (float) (tn[k] - tn[segment base of k]); device arrays indexed like the pulse table
+    const double* tn;
+    const float* xi;
 };
 
 void launch_pulse_table(const DevOrbit& orbit, Linspace in_time, const double* in_times, double fc,
@@ -88,6 +92,8 @@ void fast_tile_shape(int* tile_az, int* tile_rg);
 // that is not the last one of a call must END on such a multiple, so that every FP32 tile sum
 // holds the same pulses whatever the launch partition (bit-reproducible output).
 int fast_pulse_tile();
+// Pulses per geometry segment of the fast kernel (segments sit on absolute multiples of it).
+int fast_segment();
 // The pulse table holds records for pulses [-kPulsePadLo, n_pulses + kPulsePadHi): the entries
 // outside the input grid are orbit EXTRAPOLATIONS (smooth continuation), used by the fast
 // kernel's segment-boundary evaluations and by staged tiles that run over the ends.
