@@ -75,7 +75,7 @@ enum { I3B_ORBIT_HERMITE = 0, I3B_ORBIT_LEGENDRE = 1 };
 /* isce3::core::dataInterpMethod (cxx/isce3/core/Constants.h) subset usable by
  * LUT2d / DEMInterpolator on this path.                                    */
 enum {
-    I3B_INTERP_SINC = 0, /* not supported -> I3B_EXC_INVALID_ARGUMENT */
+    I3B_INTERP_SINC = 0, /* Sinc2dInterpolator(SINC_LEN = 8, SINC_SUB = 8192) */
     I3B_INTERP_BILINEAR = 1,
     I3B_INTERP_BICUBIC = 2,
     I3B_INTERP_NEAREST = 3,
@@ -395,6 +395,27 @@ int i3b_rangecomp_query(const I3B_RangeComp* rc, int* fft_size, int* output_size
  * following i3b_backproject with the same flag).                              */
 int i3b_rangecomp_execute(I3B_RangeComp* rc, float* out, const float* in, int batch,
                           uint32_t flags);
+/* Radiometric corrections the workflow applies to every range-compressed block on the host
+ * (nisar/workflows/focus.py:1956-1975), fused into the pass that writes the output:
+ *   out[b][j] = rc[b][j] * column_scale[j] / interp(slant_ranges[j]; pattern_ranges, patterns[b])
+ * column_scale: the per-column factors multiplied together -- baseband shift phasors
+ * `deramp_rc` and range-loss `slant_ranges / ref_range` -- complex64 [output_size] or NULL;
+ * the dynamic antenna pattern of each line, given on the coarse axis pattern_ranges, is
+ * interpolated like numpy.interp (linear, clamped) onto slant_ranges.  Set once with
+ * i3b_rangecomp_set_scaling (NULL clears); the per-line pattern samples travel with each
+ * execute call (complex64 [batch][n_pattern], NULL: no pattern division for that call).    */
+typedef struct {
+    const float* column_scale;    /* complex64 [output_size] or NULL                      */
+    const double* slant_ranges;   /* [output_size]: slant range of every output sample    */
+    const double* pattern_ranges; /* [n_pattern], increasing                              */
+    int32_t n_pattern;            /* 0: no antenna-pattern division                       */
+    int32_t _pad;
+} I3B_RangeCompScaling;
+int i3b_rangecomp_set_scaling(I3B_RangeComp* rc, const I3B_RangeCompScaling* scaling);
+int i3b_rangecomp_execute_scaled(I3B_RangeComp* rc, float* out, const float* in, int batch,
+                                 uint32_t flags, const float* patterns);
+int i3b_rangecomp_execute_to_device_scaled(I3B_RangeComp* rc, const float* in, int64_t lines,
+                                           const float* patterns, float** dev_out);
 /* Range-compress `lines` host lines (any number: processed in chunks of maxbatch) into ONE
  * newly allocated device array complex64 [lines][output_size], returned in *dev_out and owned
  * by the caller (i3b_device_free); feed it to i3b_backproject with I3B_FLAG_DEVICE_INPUT.   */

@@ -81,6 +81,13 @@ backproject(std::complex<float>* out, const isce3::container::RadarGeometry& out
             const isce3::geometry::detail::Rdr2GeoBracketParams& r2g,
             const isce3::geometry::detail::Geo2RdrBracketParams& g2r, int batch, float* height)
 {
+    // Backproject.cpp:88-92 / Backproject.cu:480-484, compared on the DateTime values themselves
+    // (the descriptor carries the epoch as seconds + fraction, a double near 1.7e9 only
+    // resolves ~2.4e-7 s)
+    if (out_geometry.referenceEpoch() != in_geometry.referenceEpoch()) {
+        throw isce3::except::RuntimeError(ISCE_SRCINFO(),
+                "input reference epoch must match output reference epoch");
+    }
     I3B_BackprojectArgs a {};
     a.abi_version = I3B_ABI_VERSION;
     a.out = reinterpret_cast<float*>(out);

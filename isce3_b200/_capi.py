@@ -218,6 +218,16 @@ FIT_MAX_TAP_PAIRS = 17
 FIT_MAX_COEF = 4
 
 
+class RangeCompScaling(C.Structure):
+    _fields_ = [
+        ("column_scale", C.c_void_p),
+        ("slant_ranges", C.c_void_p),
+        ("pattern_ranges", C.c_void_p),
+        ("n_pattern", C.c_int32),
+        ("_pad", C.c_int32),
+    ]
+
+
 class TapPolyFit(C.Structure):
     _fields_ = [
         ("taps", C.c_int32),
@@ -255,6 +265,9 @@ EXPORTED_SYMBOLS = (
     "i3b_rangecomp_query",
     "i3b_rangecomp_execute",
     "i3b_rangecomp_execute_to_device",
+    "i3b_rangecomp_set_scaling",
+    "i3b_rangecomp_execute_scaled",
+    "i3b_rangecomp_execute_to_device_scaled",
     "i3b_device_free",
     "i3b_device_to_host",
     "i3b_rangecomp_last_device_ms",
@@ -325,6 +338,13 @@ def load_library() -> C.CDLL:
     lib.i3b_rangecomp_execute.restype = C.c_int
     lib.i3b_rangecomp_execute_to_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]
     lib.i3b_rangecomp_execute_to_device.restype = C.c_int
+    lib.i3b_rangecomp_set_scaling.argtypes = [C.c_void_p, C.c_void_p]
+    lib.i3b_rangecomp_set_scaling.restype = C.c_int
+    lib.i3b_rangecomp_execute_scaled.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_void_p]
+    lib.i3b_rangecomp_execute_scaled.restype = C.c_int
+    lib.i3b_rangecomp_execute_to_device_scaled.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                                           C.POINTER(C.c_void_p)]
+    lib.i3b_rangecomp_execute_to_device_scaled.restype = C.c_int
     lib.i3b_device_free.argtypes = [C.c_void_p]
     lib.i3b_device_free.restype = C.c_int
     lib.i3b_device_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]

@@ -330,8 +330,6 @@ class LUT2d:
         data = np.ascontiguousarray(data, dtype=np.float64)
         if data.ndim != 2:
             raise ValueError("LUT2d data must be 2-D")
-        if self.interp_method == DataInterpMethod.SINC:
-            raise ValueError("sinc LUT2d interpolation is not supported on the TDBP path")
         self.data = data
         self.have_data = True
         self.ref_value = float(data[0, 0])  # LUT2d.cpp:121

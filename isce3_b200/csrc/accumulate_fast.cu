@@ -172,6 +172,7 @@ struct FastParams {
     int tiles_rg, tiles_az;
     int tile_j0;    // first tile row of this launch (tiles_az counts the rows of the launch)
     int k_landed;   // pulses below this index are on the device (0: no such limit)
+    int seg;        // pulses per geometry segment (a power of two, multiple of TK)
     double G;       // samples per cycle: 1 / (fc * dtau)
     double U0;      // swst / dtau
     double fc;
@@ -414,31 +415,32 @@ struct PairState {
     f32x2 ang0;        // 2*pi*(carrier phase in cycles at the segment base, reduced to [-1/2, 1/2])
     f32x2 f0m;         // frac(sample coordinate at the segment base) - 1/2 - Gr * ang0
     f32x2 c1, c2, c3;  // carrier phase increment over the segment: ((c3 j + c2) j + c1) j  [rad]
+    f32x2 c1l;         // c1 = c1 + c1l to twice the precision (the term that reaches hundreds of rad)
     int i0rel[PX];     // window start at the base minus the magic bias (window origin added per tile)
     f32x2 accp[PX], accq[PX]; // FP32 partial sums of the pulse tile: sum cos*(re,im), sum sin*(re,im)
-    int kstart[PX], kspan[PX]; // aperture: kstart <= k < kstart + kspan
     float flim;        // steady sub-tiles: 1/2 - bound on what the cubic's curvature adds between checks
 };
 
 // Pulses per geometry segment (one exact FP64 phase evaluation per pixel per segment, a cubic
-// in between).  128: the cubic's own error stays ~1e-6 rad (spaceborne) / ~1e-5 rad (airborne),
-// the FP32 evaluation error doubles to ~2e-5 rad at the end of a segment (relative RMS of the
-// image 8e-6 instead of 4e-6; gate 1e-4), the FP64 work per pulse halves: +2 % throughput.
+// in between): a run-time parameter, 128 or 64 -- the host takes 128 where the cubic's own
+// error (0.0234 h^4 |d4 phase / dt4|, h = segment duration) stays below ~2e-6 rad (orbital
+// geometries) and 64 otherwise (airborne: 1.4e-5 rad at 128).  FP32 evaluation error does not
+// grow with the segment length any more (see RunPoly).  I3B_SEG forces a value (experiments).
 #ifndef I3B_SEG
-#define I3B_SEG 128
+#define I3B_SEG 0
 #endif
-#ifndef I3B_KK_UNROLL
-#define I3B_KK_UNROLL 4
-#endif
-constexpr int SEG = I3B_SEG; // pulses per geometry segment
+constexpr int SEG_MAX = 128; // pulses per geometry segment, at most (pulse-table padding)
 #ifndef I3B_SUB
 #define I3B_SUB 8
 #endif
 constexpr int SUB = I3B_SUB;      // pulses per run (steady / per-pulse / aperture-edge path chosen per run)
 constexpr int EDGE_RUN = SUB;
 static_assert(TK % SUB == 0, "a staged pulse tile is a whole number of runs");
+#ifndef I3B_KK_UNROLL
+#define I3B_KK_UNROLL 4
+#endif
 constexpr int KK_UNROLL = I3B_KK_UNROLL;
-static_assert(SEG % TK == 0, "a geometry segment is a whole number of staged pulse tiles");
+static_assert(64 % TK == 0, "a geometry segment is a whole number of staged pulse tiles");
 constexpr float MAGIC32 = 12582912.0f;         // 1.5 * 2^23: float -> nearest integer by addition
 constexpr int MAGIC32_BITS = 0x4B400000;
 
@@ -590,6 +592,43 @@ struct ChunkedMac {
     }
 };
 
+// Carrier phase of the pixel pair over ONE run of pulses, re-centred on the run's first pulse:
+//   ang(x) = A0 + A1 x + A2 x^2 + A3 x^3,   x = position on the segment axis - that of the run start
+// with A0 reduced modulo 2 pi.  Over a 128-pulse segment the unreduced phase reaches hundreds of
+// radians, where an FP32 value resolves 3e-5 rad and the SFU's own range reduction another
+// 2e-5: per-pulse errors that do not average out on noise-like scenes (relative RMS 6e-5 ...
+// 8e-5 measured on the 80 MHz / airborne frames).  Here the one large term, c1 * j, is formed
+// exactly (FMA two-product, c1 carried as a float pair), whole turns are removed (Cody-Waite
+// split of 2 pi) and everything the pulse loop evaluates stays below ~40 rad.  `f0m` is the
+// sample-coordinate offset adjusted for the removed turns (coordinate = f0m + Gr * ang).
+struct RunPoly {
+    f32x2 A0, A1, A2, A3, f0m;
+};
+constexpr float INV_TWO_PI_F = 0.15915494309189535f;
+constexpr float TWO_PI_HI_F = 6.28125f;                  // 201 / 32: n * hi is exact
+constexpr float TWO_PI_LO_F = 0.0019353071795864769f;    // 2 pi - hi
+
+__device__ __forceinline__ RunPoly make_run_poly(const PairState& S, float js, float G)
+{
+    RunPoly R;
+    const f32x2 js2 = bcast2(js);
+    const f32x2 nq = mul2(S.c1, bcast2(-js));             // -(c1 js), rounded
+    f32x2 e = fma2(S.c1, js2, nq);                        // c1 js + nq: the rounding error, exact
+    e = fma2(S.c1l, js2, e);
+    const f32x2 t = fma2(nq, bcast2(-INV_TWO_PI_F), bcast2(MAGIC32));
+    const f32x2 n = add2(t, bcast2(-MAGIC32));            // whole turns in c1 js
+    const f32x2 rneg = fma2(n, bcast2(TWO_PI_HI_F), nq);  // -(c1 js - n 2pi_hi)
+    f32x2 rest = fma2(fma2(S.c3, js2, S.c2), mul2(js2, js2), add2(S.ang0, e));
+    rest = fma2(n, bcast2(-TWO_PI_LO_F), rest);
+    R.A0 = sub2(rest, rneg);
+    const f32x2 c3x3 = mul2(S.c3, bcast2(3.0f)), c2x2 = add2(S.c2, S.c2);
+    R.A2 = fma2(c3x3, js2, S.c2);
+    R.A1 = fma2(fma2(c3x3, js2, c2x2), js2, S.c1);
+    R.A3 = S.c3;
+    R.f0m = fma2(n, bcast2(G), S.f0m);                    // Gr * 2 pi n = G n samples
+    return R;
+}
+
 // One staged pulse tile (TK pulses) for the thread's pixel pair.  EDGE = false: every pixel
 // of the CTA integrates every pulse of the tile (no aperture test in the loop).
 //
@@ -598,13 +637,18 @@ struct ChunkedMac {
 // FADD 1.4, LOP3 / IADD3 / VIMNMX 0.6-0.9, MOV / LDS ~0.2 (issue in the FFMA2 shadow), MUFU 8
 // XU cycles (asynchronous).  So the loop is written to be FFMA2-only on the FMA pipe.
 template<int K, int D, class Coef, bool EDGE, int NP>
-__device__ __forceinline__ void tile_body(PairState& S, float& jf, unsigned& jjmax,
+__device__ __forceinline__ void tile_body(PairState& S, const RunPoly& R, float js, unsigned& jjmax,
                                           uint32_t lines_addr, uint32_t row_bytes, int wlo,
                                           unsigned jmax, float Gr, unsigned krel0, unsigned krel1,
-                                          int zero, uint32_t bank, const float* __restrict__ xi = nullptr)
+                                          int zero, uint32_t bank, const float* __restrict__ xi = nullptr,
+                                          unsigned kspan0 = 0u, unsigned kspan1 = 0u)
 {
+    // krel / kspan (EDGE only): pulse index of the run's first pulse relative to each pixel's
+    // aperture start, and the aperture lengths -- pulses outside are skipped.
     // xi (non-uniform pulse times only): position of each pulse of the run on the segment's
-    // time axis, in nominal pulse intervals -- replaces the pulse index in the phase cubic
+    // time axis, in nominal pulse intervals (js = that of the run's first pulse) -- replaces
+    // the pulse index in the phase polynomial
+    float xf = 0.f;
     typedef Weights<K, D, Coef> WT;
     typename WT::Top top;
     WT::load_top(top, zero, bank);
@@ -618,13 +662,13 @@ __device__ __forceinline__ void tile_body(PairState& S, float& jf, unsigned& jjm
         // from the shared-memory base every pulse: ~10 instructions)
         asm volatile("" : "+r"(line_addr));
         // carrier phase [rad] (reduced at the segment base) of both pixels at once
-        if (xi) jf = __ldg(xi + kk);
-        const f32x2 j2 = bcast2(jf);
-        const f32x2 ang = fma2(fma2(fma2(S.c3, j2, S.c2), j2, S.c1), j2, S.ang0);
-        const f32x2 g = fma2(ang, bcast2(Gr), S.f0m); // sample coordinate - floor(base) - 1/2
+        if (xi) xf = __ldg(xi + kk) - js;
+        const f32x2 x2 = bcast2(xf);
+        const f32x2 ang = fma2(fma2(fma2(R.A3, x2, R.A2), x2, R.A1), x2, R.A0);
+        const f32x2 g = fma2(ang, bcast2(Gr), R.f0m); // sample coordinate - floor(base) - 1/2
         const f32x2 m = add2(g, bcast2(MAGIC32));     // nearest integer of g == floor(coordinate)
         const f32x2 f = sub2(g, add2(m, bcast2(-MAGIC32))); // centred fraction in [-1/2, 1/2]
-        jf += 1.0f;
+        xf += 1.0f;
         float m0, m1, ang0, ang1;
         unpack2(m, m0, m1);
         unpack2(ang, ang0, ang1);
@@ -634,8 +678,8 @@ __device__ __forceinline__ void tile_body(PairState& S, float& jf, unsigned& jjm
         const unsigned j0 = min(jj0, jmax), j1 = min(jj1, jmax);
         float cs0, sn0, cs1, sn1;
         // pulses outside a pixel's aperture (EDGE tiles only) are skipped at the rotation
-        const bool in0 = !EDGE || krel0 + (unsigned) kk < (unsigned) S.kspan[0];
-        const bool in1 = !EDGE || krel1 + (unsigned) kk < (unsigned) S.kspan[1];
+        const bool in0 = !EDGE || krel0 + (unsigned) kk < kspan0;
+        const bool in1 = !EDGE || krel1 + (unsigned) kk < kspan1;
         sincos_fast(ang0, sn0, cs0);
         sincos_fast(ang1, sn1, cs1);
         if constexpr (K >= 16 && K % 8 == 0) {
@@ -696,12 +740,14 @@ __device__ __noinline__
 #else
 __device__ __forceinline__
 #endif
-unsigned tile_body_edge(PairState& S, float jf, unsigned jjmax, uint32_t lines_addr,
+unsigned tile_body_edge(PairState& S, RunPoly R, float js, unsigned jjmax, uint32_t lines_addr,
                         uint32_t row_bytes, int wlo, unsigned jmax, float Gr, unsigned krel0,
-                        unsigned krel1, int zero, uint32_t bank, const float* __restrict__ xi)
+                        unsigned krel1, int zero, uint32_t bank, const float* __restrict__ xi,
+                        unsigned kspan0, unsigned kspan1)
 {
-    // (jf, jjmax by value: only the pair state has to live in memory around the call)
-    tile_body<K, D, Coef, true, EDGE_RUN>(S, jf, jjmax, lines_addr, row_bytes, wlo, jmax, Gr, krel0, krel1, zero, bank, xi);
+    // (the run polynomial and jjmax by value: only the pair state has to live in memory around the call)
+    tile_body<K, D, Coef, true, EDGE_RUN>(S, R, js, jjmax, lines_addr, row_bytes, wlo, jmax, Gr, krel0, krel1, zero, bank, xi,
+                                          kspan0, kspan1);
     return jjmax;
 }
 
@@ -916,8 +962,6 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, const __grid_
             if (r.kstart < 0) bad = true;
             const int ks = max(r.kstart, P.k_begin);
             const int ke_p = min(r.kstop, P.k_end);
-            S.kstart[p] = ks;
-            S.kspan[p] = max(ke_p - ks, 0);
             S.accp[p] = S.accq[p] = 0ull;
             if (ke_p > ks) {
                 kmin = min(kmin, ks);
@@ -965,6 +1009,7 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, const __grid_
     // pixel alone, so the image does not depend on how the pulses were cut into launches
     // (`batch`, upload timing) nor on how the grid was cut into shards.  The host keeps
     // launch boundaries on multiples of TK (fast_pulse_tile()).
+    const int SEG = P.seg;
     const int t0 = (kb / TK) * TK; // kb >= 0
     const int ntiles = (ke - t0 + TK - 1) / TK;
 
@@ -1036,7 +1081,7 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, const __grid_
     const unsigned jmax = (unsigned) (P.W - (K + 3));
     const double TWO_PI_D = 6.283185307179586476925;
     const float Gr = (float) (P.G / TWO_PI_D); // samples per radian of carrier phase
-    float jf = 0.f;                             // pulse index within the segment
+    const float Gsamp = (float) P.G;           // samples per cycle (turn) of carrier phase
     int seg_b = 0;                              // first pulse of the current segment
 
     for (int n = 0; n < ntiles; ++n) {
@@ -1050,7 +1095,7 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, const __grid_
             // the four surrounding boundaries, everything inside the segment is FP32 ----
             const int b = kt & ~(SEG - 1);
             seg_b = b;
-            float c1[PX], c2[PX], c3[PX], a0[PX], f0[PX];
+            float c1[PX], c1lo[PX], c2[PX], c3[PX], a0[PX], f0[PX];
 #pragma unroll
             for (int p = 0; p < PX; ++p) {
                 const PixelRec q = load_pixel(pix + gidx[p]);
@@ -1073,15 +1118,19 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, const __grid_
                     const double d03 = (y3 - y0) / (x3 - x0);
                     const double d203 = (d03 - d20) / (x3 - x2);
                     const double d1203 = (d203 - d120) / x3;
-                    c1[p] = (float) (TWO_PI_D * (d12 - d120 * x2 + d1203 * x2 * x0));
+                    const double c1d = TWO_PI_D * (d12 - d120 * x2 + d1203 * x2 * x0);
+                    c1[p] = (float) c1d;
+                    c1lo[p] = (float) (c1d - (double) c1[p]);
                     c2[p] = (float) (TWO_PI_D * (d120 - d1203 * (x2 + x0)));
                     c3[p] = (float) (TWO_PI_D * d1203);
                 } else {
                 const double d1 = y2 - y1, d2 = (y2 - y1) - (y1 - y0);
                 const double d3 = ((y3 - y2) - (y2 - y1)) - d2;
                 // p(tau) - y1 = tau (d1 - d2/2 - d3/6) + tau^2 d2/2 + tau^3 d3/6, tau = j / SEG
-                c1[p] = (float) (TWO_PI_D * (d1 - 0.5 * d2 - d3 * (1.0 / 6.0)) * (1.0 / SEG));
-                c2[p] = (float) (TWO_PI_D * (0.5 * d2) * (1.0 / (SEG * SEG)));
+                const double c1d = TWO_PI_D * (d1 - 0.5 * d2 - d3 * (1.0 / 6.0)) * (1.0 / SEG);
+                c1[p] = (float) c1d;
+                c1lo[p] = (float) (c1d - (double) c1[p]);
+                c2[p] = (float) (TWO_PI_D * (0.5 * d2) * (1.0 / ((double) SEG * SEG)));
                 c3[p] = (float) (TWO_PI_D * (d3 * (1.0 / 6.0)) * (1.0 / ((double) SEG * SEG * SEG)));
                 }
                 a0[p] = (float) (TWO_PI_D * (y1 - rint(y1)));
@@ -1091,6 +1140,7 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, const __grid_
                 S.i0rel[p] = (int) ufl + LOWOFF - MAGIC32_BITS; // window origin added per tile
             }
             S.c1 = pack2(c1[0], c1[1]);
+            S.c1l = pack2(c1lo[0], c1lo[1]);
             S.c2 = pack2(c2[0], c2[1]);
             S.c3 = pack2(c3[0], c3[1]);
             S.ang0 = pack2(a0[0], a0[1]);
@@ -1120,22 +1170,20 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, const __grid_
 #pragma unroll 1
         for (int sub = 0; sub < TK / SUB; ++sub) {
             const int kr = kt + sub * SUB; // first pulse of the run
-            const float js = (float) (kr - seg_b);
+            // position of the run's first pulse on the segment axis (pulse index, or time in
+            // nominal pulse intervals for non-uniform pulse trains)
+            const float js = P.xi ? __ldg(P.xi + kr) : (float) (kr - seg_b);
             const uint32_t la = lines_addr + (uint32_t) (sub * SUB) * row_bytes;
+            RunPoly R = make_run_poly(S, js, Gsamp);
             if (I3B_EDGE_SPLIT && kr >= ks_max && kr + SUB <= ke_min) {
                 bool steady = false;
                 // (32 taps: the rolled steady loop gains nothing over the per-pulse path, measured)
                 if constexpr (I3B_STEADY && K < I3B_STEADY_MAX_TAPS) {
-                    // phase cubic re-centred on the run: ang(js + x) = A0 + A1 x + A2 x^2 + A3 x^3
-                    const f32x2 js2 = bcast2(js), Gr2 = bcast2(Gr);
-                    const f32x2 c3x3 = mul2(S.c3, bcast2(3.0f)), c2x2 = add2(S.c2, S.c2);
-                    f32x2 A2 = fma2(c3x3, js2, S.c2);
-                    f32x2 A1 = fma2(fma2(c3x3, js2, c2x2), js2, S.c1);
-                    const f32x2 A0 = fma2(fma2(fma2(S.c3, js2, S.c2), js2, S.c1), js2, S.ang0);
+                    const f32x2 Gr2 = bcast2(Gr);
                     // coordinate (minus floor(base) + 1/2) at the first and the last pulse of the run
                     const f32x2 XE = bcast2((float) (SUB - 1));
-                    const f32x2 ange = fma2(fma2(fma2(S.c3, XE, A2), XE, A1), XE, A0);
-                    const f32x2 g0 = fma2(A0, Gr2, S.f0m), ge = fma2(ange, Gr2, S.f0m);
+                    const f32x2 ange = fma2(fma2(fma2(R.A3, XE, R.A2), XE, R.A1), XE, R.A0);
+                    const f32x2 g0 = fma2(R.A0, Gr2, R.f0m), ge = fma2(ange, Gr2, R.f0m);
                     const f32x2 mm = add2(g0, bcast2(MAGIC32));
                     const f32x2 tt = add2(mm, bcast2(-MAGIC32)); // integer part at the first pulse
                     const f32x2 fa = sub2(g0, tt), fe = sub2(ge, tt);
@@ -1151,32 +1199,40 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, const __grid_
                     steady = worst <= S.flim && jj1 == jj0 + 1u && jj0 < jmax;
                     if (steady) {
                         const uint32_t src = la + ((jj0 >> 1) << 4);
-                        const f32x2 fbase = sub2(S.f0m, tt);
+                        const f32x2 fbase = sub2(R.f0m, tt);
+                        f32x2 A1 = R.A1, A2 = R.A2;
                         if (I3B_QUAD_RUN) {
                             // quadratic through the cubic at x = 0, (SUB-1)/2, SUB-1
-                            A1 = fma2(S.c3, bcast2(-0.5f * (SUB - 1) * (SUB - 1)), A1);
-                            A2 = fma2(S.c3, bcast2(1.5f * (SUB - 1)), A2);
+                            A1 = fma2(R.A3, bcast2(-0.5f * (SUB - 1) * (SUB - 1)), A1);
+                            A2 = fma2(R.A3, bcast2(1.5f * (SUB - 1)), A2);
                         }
                         if (jj0 & 1u)
-                            subtile_steady<K, D, Coef, 1, SUB>(S, A0, A1, A2, S.c3, fbase, Gr, src, row_bytes, P.zero, poly_addr);
+                            subtile_steady<K, D, Coef, 1, SUB>(S, R.A0, A1, A2, R.A3, fbase, Gr, src, row_bytes, P.zero, poly_addr);
                         else
-                            subtile_steady<K, D, Coef, 0, SUB>(S, A0, A1, A2, S.c3, fbase, Gr, src, row_bytes, P.zero, poly_addr);
+                            subtile_steady<K, D, Coef, 0, SUB>(S, R.A0, A1, A2, R.A3, fbase, Gr, src, row_bytes, P.zero, poly_addr);
                     }
                 }
-                if (!steady) {
-                    jf = js;
-                    tile_body<K, D, Coef, false, SUB>(S, jf, jjmax, la, row_bytes, wlo, jmax, Gr, 0u, 0u, P.zero, poly_addr,
+                if (!steady)
+                    tile_body<K, D, Coef, false, SUB>(S, R, js, jjmax, la, row_bytes, wlo, jmax, Gr, 0u, 0u, P.zero, poly_addr,
                                                       P.xi ? P.xi + kr : nullptr);
-                }
             } else {
-                // k - kstart for the first pulse of the run, per pixel
-                const unsigned krel0 = (unsigned) (kr - S.kstart[0]);
-                const unsigned krel1 = (unsigned) (kr - S.kstart[1]);
+                // aperture of each pixel within this launch (re-read: edge runs are a few per
+                // pixel, their bounds do not deserve registers in the interior loops) and
+                // k - kstart for the first pulse of the run
+                unsigned krel[PX], kspan[PX];
+#pragma unroll
+                for (int p = 0; p < PX; ++p) {
+                    const PixelRec* q = pix + gidx[p];
+                    const int ks = max(q->kstart, P.k_begin), ke_p = min(q->kstop, P.k_end);
+                    krel[p] = (unsigned) (kr - ks);
+                    kspan[p] = (unsigned) max(ke_p - ks, 0);
+                }
+                const unsigned krel0 = krel[0], krel1 = krel[1];
                 // (through a copy: the out-of-line call wants its argument in memory, and the
                 // interior paths should not find their pair state there)
                 PairState T = S;
-                jjmax = tile_body_edge<K, D, Coef>(T, js, jjmax, la, row_bytes, wlo, jmax, Gr, krel0, krel1, P.zero, poly_addr,
-                                                   P.xi ? P.xi + kr : nullptr);
+                jjmax = tile_body_edge<K, D, Coef>(T, R, js, jjmax, la, row_bytes, wlo, jmax, Gr, krel0, krel1, P.zero, poly_addr,
+                                                   P.xi ? P.xi + kr : nullptr, kspan[0], kspan[1]);
                 S.accp[0] = T.accp[0]; S.accp[1] = T.accp[1];
                 S.accq[0] = T.accq[0]; S.accq[1] = T.accq[1];
             }
@@ -1555,6 +1611,7 @@ int launch_accumulate_fast(const AccumParams& P, const DevKernel& hk, const Pixe
         if (FP.tiles_az <= 0) return 0;
     }
     FP.k_landed = P.k_landed;
+    FP.seg = P.seg == 128 ? 128 : 64;
     FP.G = 1.0 / (P.fc * P.dtau);
     FP.U0 = P.swst / P.dtau;
     FP.fc = P.fc;
@@ -1595,7 +1652,17 @@ int fast_tiles(int out_lines, int out_width)
 }
 
 int fast_pulse_tile() { return TK; }
-int fast_segment() { return SEG; }
+// Segment length for a scene: the cubic through four exact phase values h = seg / prf apart
+// is off by at most 0.0234 h^4 |d4 phase / dt4|; for a platform at speed v passing a target at
+// range r that derivative is at most (4 pi / wavelength) 3 v^4 / r^3 (broadside; x4 for margin).
+int fast_segment(double wavelength, double prf, double v_max, double r_min)
+{
+    if (I3B_SEG) return I3B_SEG;
+    if (!(wavelength > 0) || !(prf > 0) || !(v_max > 0) || !(r_min > 0)) return 64;
+    const double d4 = 4.0 * (4.0 * M_PI / wavelength) * 3.0 * std::pow(v_max, 4) / std::pow(r_min, 3);
+    const double h = 128.0 / prf;
+    return 0.0234 * std::pow(h, 4) * d4 <= 2e-6 ? 128 : 64;
+}
 
 void fast_tile_shape(int* tile_az, int* tile_rg)
 {

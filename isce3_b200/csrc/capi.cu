@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "launch.h"
+#include "sinc_table.h"
 
 namespace i3b {
 
@@ -248,6 +249,18 @@ struct HostScene {
     std::vector<int> devices;
 };
 
+static int scene_segment(const I3B_BackprojectArgs& a)
+{
+    const I3B_Orbit& o = a.in_geometry.orbit;
+    double vmax = 0;
+    for (int i = 0; i < o.n; ++i) {
+        const double* v = o.vel + 3 * (size_t) i;
+        vmax = std::max(vmax, std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]));
+    }
+    const double r_min = std::min(a.in_geometry.grid.starting_range, a.out_geometry.grid.starting_range);
+    return fast_segment(kC / a.fc, a.in_geometry.grid.prf, vmax, r_min);
+}
+
 static void validate(const I3B_BackprojectArgs& a)
 {
     auto bad = [](const std::string& m) { throw ApiError(I3B_EXC_INVALID_ARGUMENT, m); };
@@ -273,7 +286,6 @@ static void validate(const I3B_BackprojectArgs& a)
         if (g->doppler.have_data) {
             if (!g->doppler.data || g->doppler.length < 1 || g->doppler.width < 1)
                 bad("Doppler LUT has no data");
-            if (g->doppler.method == I3B_INTERP_SINC) bad("sinc LUT2d interpolation is not supported");
         }
     }
     if (a.dem.have_raster) {
@@ -282,7 +294,6 @@ static void validate(const I3B_BackprojectArgs& a)
         if (!proj_setup(a.dem.epsg, kA, kE2, &pj))
             bad("unknown EPSG code for a raster DEM: " + std::to_string(a.dem.epsg) +
                 " (supported: 4326, UTM 326xx/327xx, 3031, 3413, 6933)");
-        if (a.dem.method == I3B_INTERP_SINC) bad("sinc DEM interpolation is not supported");
     }
     if (!(a.fc > 0) || !(a.ds > 0)) bad("fc and ds must be positive");
     if (a.pulse_times) {
@@ -365,7 +376,7 @@ struct Shard {
     } streams;
     cudaStream_t& compute = streams.compute;
     cudaStream_t& copy = streams.copy;
-    DevBuf<double> out_pos, out_vel, in_pos, in_vel, out_dop, in_dop, pv, times, tn;
+    DevBuf<double> out_pos, out_vel, in_pos, in_vel, out_dop, in_dop, pv, times, tn, sinc;
     DevBuf<float> xi;
     DevBuf<float> dem, kdata, height;
     DevBuf<PulseRec> pulse;
@@ -445,11 +456,21 @@ static void shard_setup(const HostScene& hs, Shard& sh)
     if (a.range_cor) sh.range_cor.upload(reinterpret_cast<const float2*>(a.range_cor), (size_t) og.grid.width, s);
     sh.range_cor_view = sh.range_cor.p;
 
+    // 2-D sinc interpolation of a LUT / the DEM: the reference's kernel table (512 KB), once
+    const bool any_sinc = (og.doppler.have_data && og.doppler.method == I3B_INTERP_SINC) ||
+                          (ig.doppler.have_data && ig.doppler.method == I3B_INTERP_SINC) ||
+                          (a.dem.have_raster && a.dem.method == I3B_INTERP_SINC);
+    if (any_sinc) {
+        static const std::vector<double> table = make_sinc_table();
+        sh.sinc.upload(table.data(), table.size(), s);
+    }
+    const double* sinc_dev = sh.sinc.p;
     auto dev_orbit = [](const I3B_Orbit& o, const double* p, const double* v) {
         return DevOrbit {o.t0, o.dt, o.n, o.method, p, v};
     };
-    auto dev_lut = [](const I3B_LUT2d& l, const double* d) {
+    auto dev_lut = [sinc_dev](const I3B_LUT2d& l, const double* d) {
         DevLUT2d r;
+        r.sinc = sinc_dev;
         r.have_data = l.have_data; r.bounds_error = l.bounds_error; r.method = l.method;
         r.length = (int) l.length; r.width = (int) l.width;
         r.ref_value = l.ref_value; r.xstart = l.xstart; r.ystart = l.ystart; r.dx = l.dx; r.dy = l.dy;
@@ -475,6 +496,7 @@ static void shard_setup(const HostScene& hs, Shard& sh)
     P.dem.length = (int) a.dem.length; P.dem.width = (int) a.dem.width;
     P.dem.ref_height = a.dem.ref_height; P.dem.xstart = a.dem.xstart; P.dem.ystart = a.dem.ystart;
     P.dem.dx = a.dem.dx; P.dem.dy = a.dem.dy; P.dem.data = sh.dem.p;
+    P.dem.sinc = sinc_dev;
     proj_setup(a.dem.have_raster ? a.dem.epsg : 4326, kA, kE2, &P.dem.proj);
     P.r2g = a.rdr2geo;
     P.g2r = a.geo2rdr;
@@ -522,6 +544,7 @@ static void shard_setup(const HostScene& hs, Shard& sh)
     sh.use_fast = !(a.flags & I3B_FLAG_FORCE_GENERIC) && fast_fit(sh.host_kernel, &fit, why, sizeof why);
     // Non-uniform pulse trains: the fast kernel's phase cubic runs over TIME (positions tn / xi
     // of the pulses on the segment's time axis) instead of the pulse index.
+    A.seg = scene_segment(a);
     A.tn = hs.pulse_times.empty() ? nullptr : sh.tn.p + kPulsePadLo;
     A.xi = hs.pulse_times.empty() ? nullptr : sh.xi.p + kPulsePadLo;
     sh.fast_variant = sh.use_fast ? fit.imm_variant : -1;
@@ -1027,7 +1050,7 @@ static std::unique_ptr<I3B_Plan> make_plan(const I3B_BackprojectArgs* args, bool
                         k < 0 ? T[0] + (double) k * d0 : (k >= n ? T[n - 1] + (double) (k - n + 1) * d1 : T[k]);
             // the fast kernel's time axis: nominal pulse intervals, relative to each pulse's
             // geometry-segment base (absolute multiples of the segment length)
-            const int seg = fast_segment();
+            const int seg = scene_segment(*args);
             hs.pulse_tn.resize(hs.pulse_times.size());
             hs.pulse_xi.resize(hs.pulse_times.size());
             for (size_t i = 0; i < hs.pulse_times.size(); ++i) hs.pulse_tn[i] = hs.pulse_times[i] * g.prf;
@@ -1192,7 +1215,7 @@ namespace {
 
 struct GeomBatch {
     cudaStream_t s = nullptr;
-    DevBuf<double> pos, vel, lut;
+    DevBuf<double> pos, vel, lut, sinc;
     DevBuf<float> dem;
     DevBuf<DevStatus> status;
     ~GeomBatch()
@@ -1672,8 +1695,11 @@ int i3b_rdr2geo_bracket_batch(const I3B_Orbit* orbit, const I3B_DEM* dem, double
         if (dem->have_raster) {
             if (!dem->data || dem->length < 4 || dem->width < 4)
                 throw ApiError(I3B_EXC_INVALID_ARGUMENT, "DEM raster too small");
-            if (dem->method == I3B_INTERP_SINC)
-                throw ApiError(I3B_EXC_INVALID_ARGUMENT, "sinc DEM interpolation is not supported");
+            if (dem->method == I3B_INTERP_SINC) {
+                static const std::vector<double> table = make_sinc_table();
+                g.sinc.upload(table.data(), table.size(), g.s);
+                d.sinc = g.sinc.p;
+            }
             if (!proj_setup(dem->epsg, kA, kE2, &d.proj))
                 throw ApiError(I3B_EXC_INVALID_ARGUMENT, "unknown EPSG code for a raster DEM");
             g.dem.upload(dem->data, (size_t) dem->length * dem->width, g.s);
@@ -1730,8 +1756,11 @@ int i3b_geo2rdr_bracket_batch(const I3B_Orbit* orbit, const I3B_LUT2d* doppler, 
         if (doppler->have_data) {
             if (!doppler->data || doppler->length < 1 || doppler->width < 1)
                 throw ApiError(I3B_EXC_INVALID_ARGUMENT, "Doppler LUT has no data");
-            if (doppler->method == I3B_INTERP_SINC)
-                throw ApiError(I3B_EXC_INVALID_ARGUMENT, "sinc LUT2d interpolation is not supported");
+            if (doppler->method == I3B_INTERP_SINC) {
+                static const std::vector<double> table = make_sinc_table();
+                g.sinc.upload(table.data(), table.size(), g.s);
+                l.sinc = g.sinc.p;
+            }
             g.lut.upload(doppler->data, (size_t) doppler->length * doppler->width, g.s);
             l.data = g.lut.p;
         }

@@ -48,6 +48,7 @@ struct DevLUT2d {
     int length, width;
     double ref_value, xstart, ystart, dx, dy;
     const double* data;
+    const double* sinc; // method SINC: normalised kernel table [SINC_SUB][SINC_LEN] (sinc_table.h)
 };
 
 struct DevDEM {
@@ -56,6 +57,7 @@ struct DevDEM {
     double ref_height, xstart, ystart, dx, dy;
     const float* data;
     DevProj proj; // forward projection of the raster's CRS (set up on the host)
+    const double* sinc; // method SINC: normalised kernel table [SINC_SUB][SINC_LEN]
 };
 
 struct DevKernel {

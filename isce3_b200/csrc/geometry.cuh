@@ -326,9 +326,34 @@ __device__ inline U biquintic(double x, double y, const G& z)
     return spline_eval<U, N>(y - i0, HC, R);
 }
 
+// Sinc2dInterpolator::interp_impl / _sinc_eval_2d (core/Sinc2dInterpolator.cpp:45-101): 8 x 8
+// taps from the table row nearest below the fractional offset; 0 within half a kernel of the
+// array edges.
 template<typename U, class G>
-__device__ inline U interp2d(int method, double x, double y, const G& z)
+__device__ inline U sinc2d(double x, double y, const G& z, const double* __restrict__ kern)
 {
+    constexpr int LEN = 8, HALF = 4, SUB = 8192;
+    const int ix = (int) floor(x), iy = (int) floor(y);
+    const double fx = x - ix, fy = y - iy;
+    if (ix < HALF - 1 || ix > z.cols - HALF - 1) return U(0);
+    if (iy < HALF - 1 || iy > z.rows - HALF - 1) return U(0);
+    const int xx = ix + HALF, yy = iy + HALF;
+    const int ifx = min(max(0, (int) (fx * SUB)), SUB - 1), ify = min(max(0, (int) (fy * SUB)), SUB - 1);
+    const double* kx = kern + (size_t) ifx * LEN;
+    const double* ky = kern + (size_t) ify * LEN;
+    U ret(0);
+    for (int i = 0; i < LEN; ++i) {
+        const U wy = U(ky[i]);
+#pragma unroll
+        for (int j = 0; j < LEN; ++j) ret += z(yy - i, xx - j) * wy * U(kx[j]);
+    }
+    return ret;
+}
+
+template<typename U, class G>
+__device__ inline U interp2d(int method, double x, double y, const G& z, const double* sinc = nullptr)
+{
+    if (method == I3B_INTERP_SINC && sinc) return sinc2d<U, G>(x, y, z, sinc);
     switch (method) {
     case I3B_INTERP_BICUBIC: return bicubic<U, G>(x, y, z);
     case I3B_INTERP_BIQUINTIC: return biquintic<U, G>(x, y, z);
@@ -347,7 +372,7 @@ __device__ inline double lut2d_eval(const DevLUT2d& l, double y, double x)
     xi = fmin(fmax(xi, 0.0), l.width - 1.0);
     yi = fmin(fmax(yi, 0.0), l.length - 1.0);
     const Grid2d<double, true> g {l.data, l.length, l.width};
-    return interp2d<double, Grid2d<double, true>>(l.method, xi, yi, g);
+    return interp2d<double, Grid2d<double, true>>(l.method, xi, yi, g, l.sinc);
 }
 
 // LUT2d::contains (core/LUT2d.h:84-95)
@@ -385,7 +410,7 @@ __device__ inline double dem_interp_lonlat(const DevDEM& d, double lon, double l
     if (irow < 2 || irow >= d.length - 1) return d.ref_height;
     if (icol < 2 || icol >= d.width - 1) return d.ref_height;
     const Grid2d<float> g {d.data, d.length, d.width};
-    return interp2d<float, Grid2d<float>>(d.method, col, row, g);
+    return interp2d<float, Grid2d<float>>(d.method, col, row, g, d.sinc);
 }
 
 // ---- Brent's bracketing root finder ---------------------------------------------

@@ -58,6 +58,7 @@ struct AccumParams {
     // (float) (tn[k] - tn[segment base of k]); device arrays indexed like the pulse table
     const double* tn;
     const float* xi;
+    int seg; // pulses per geometry segment of the fast kernel (fast_segment())
 };
 
 void launch_pulse_table(const DevOrbit& orbit, Linspace in_time, const double* in_times, double fc,
@@ -92,8 +93,9 @@ void fast_tile_shape(int* tile_az, int* tile_rg);
 // that is not the last one of a call must END on such a multiple, so that every FP32 tile sum
 // holds the same pulses whatever the launch partition (bit-reproducible output).
 int fast_pulse_tile();
-// Pulses per geometry segment of the fast kernel (segments sit on absolute multiples of it).
-int fast_segment();
+// Pulses per geometry segment of the fast kernel for a scene (64 or 128; segments sit on
+// absolute multiples of it): radar wavelength, PRF, fastest platform speed, nearest range.
+int fast_segment(double wavelength, double prf, double v_max, double r_min);
 // The pulse table holds records for pulses [-kPulsePadLo, n_pulses + kPulsePadHi): the entries
 // outside the input grid are orbit EXTRAPOLATIONS (smooth continuation), used by the fast
 // kernel's segment-boundary evaluations and by staged tiles that run over the ends.

@@ -105,6 +105,38 @@ __global__ void rc_crop_kernel(float2* __restrict__ out, const float2* __restric
     }
 }
 
+// out[b][j] = work[b][offset + j] * col[j] / interp(pattern[b])[j]: the crop with the
+// workflow's radiometric corrections fused in (nisar/workflows/focus.py:1956-1975: baseband
+// shift `*= deramp_rc[None, :]`, dynamic antenna pattern `/= np.interp(slant_ranges, pat_ranges,
+// patterns[pulse])` per line, range-loss `*= slant_ranges / ref_range`).  col (optional) is the
+// product of the per-column factors; pat_idx / pat_w (optional) are np.interp's interval and
+// weight of every output column on the pattern's range axis, pattern[b] the line's complex samples.
+__global__ void rc_crop_scale_kernel(float2* __restrict__ out, const float2* __restrict__ work, int n_out,
+                                     int nfft, int offset, long long total, const float2* __restrict__ col,
+                                     const int* __restrict__ pat_idx, const float* __restrict__ pat_w,
+                                     const float2* __restrict__ pattern, int n_pat)
+{
+    for (long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long) gridDim.x * blockDim.x) {
+        const long long b = t / n_out;
+        const int j = (int) (t - b * n_out);
+        float2 v = work[b * nfft + offset + j];
+        if (col) {
+            const float2 c = col[j];
+            v = make_float2(v.x * c.x - v.y * c.y, v.x * c.y + v.y * c.x);
+        }
+        if (pattern) {
+            const int i = pat_idx[j];
+            const float w = pat_w[j];
+            const float2 p0 = pattern[b * n_pat + i], p1 = pattern[b * n_pat + min(i + 1, n_pat - 1)];
+            const float px = p0.x + w * (p1.x - p0.x), py = p0.y + w * (p1.y - p0.y);
+            const float d = px * px + py * py;
+            v = make_float2((v.x * px + v.y * py) / d, (v.y * px - v.x * py) / d);
+        }
+        out[t] = v;
+    }
+}
+
 } // namespace i3b
 
 using namespace i3b;
@@ -116,6 +148,12 @@ struct I3B_RangeComp {
     float2 *d_ref = nullptr, *d_work = nullptr, *d_in = nullptr, *d_out = nullptr;
     std::map<int, cufftHandle> plans; // by batch size
     double ms_last = 0.0;
+    // fused radiometric corrections (i3b_rangecomp_set_scaling)
+    float2* d_col = nullptr;
+    int* d_pat_idx = nullptr;
+    float* d_pat_w = nullptr;
+    float2* d_pattern = nullptr; // [max_batch][n_pat]
+    int n_pat = 0;
 
     cufftHandle plan_for(int batch)
     {
@@ -136,6 +174,10 @@ struct I3B_RangeComp {
         cudaFree(d_work);
         cudaFree(d_in);
         cudaFree(d_out);
+        cudaFree(d_col);
+        cudaFree(d_pat_idx);
+        cudaFree(d_pat_w);
+        cudaFree(d_pattern);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -226,7 +268,84 @@ int i3b_rangecomp_query(const I3B_RangeComp* rc, int* fft_size, int* out_size, i
     return 0;
 }
 
+int i3b_rangecomp_set_scaling(I3B_RangeComp* rc, const I3B_RangeCompScaling* sc)
+{
+    return rc_guarded([&]() {
+        if (!rc) throw RcError(I3B_EXC_INVALID_ARGUMENT, "null handle");
+        RC_CK(cudaSetDevice(rc->device));
+        RC_CK(cudaStreamSynchronize(rc->stream));
+        cudaFree(rc->d_col); rc->d_col = nullptr;
+        cudaFree(rc->d_pat_idx); rc->d_pat_idx = nullptr;
+        cudaFree(rc->d_pat_w); rc->d_pat_w = nullptr;
+        cudaFree(rc->d_pattern); rc->d_pattern = nullptr;
+        rc->n_pat = 0;
+        if (!sc) return 0;
+        const int n_out = rc->out_size;
+        if (sc->column_scale) {
+            RC_CK(cudaMalloc(&rc->d_col, (size_t) n_out * sizeof(float2)));
+            RC_CK(cudaMemcpy(rc->d_col, sc->column_scale, (size_t) n_out * sizeof(float2), cudaMemcpyHostToDevice));
+        }
+        if (sc->n_pattern > 0) {
+            if (!sc->slant_ranges || !sc->pattern_ranges)
+                throw RcError(I3B_EXC_INVALID_ARGUMENT, "antenna pattern needs slant_ranges and pattern_ranges");
+            const int np = sc->n_pattern;
+            for (int i = 1; i < np; ++i)
+                if (!(sc->pattern_ranges[i] > sc->pattern_ranges[i - 1]))
+                    throw RcError(I3B_EXC_INVALID_ARGUMENT, "pattern_ranges must be increasing");
+            // numpy.interp: clamped at both ends, linear in between
+            std::vector<int> idx(n_out);
+            std::vector<float> w(n_out);
+            for (int j = 0; j < n_out; ++j) {
+                const double x = sc->slant_ranges[j];
+                if (!(x > sc->pattern_ranges[0])) {
+                    idx[j] = 0;
+                    w[j] = 0.f;
+                } else if (!(x < sc->pattern_ranges[np - 1])) {
+                    idx[j] = np - 1;
+                    w[j] = 0.f;
+                } else {
+                    const int i = (int) (std::upper_bound(sc->pattern_ranges, sc->pattern_ranges + np, x) -
+                                         sc->pattern_ranges) - 1;
+                    idx[j] = i;
+                    w[j] = (float) ((x - sc->pattern_ranges[i]) / (sc->pattern_ranges[i + 1] - sc->pattern_ranges[i]));
+                }
+            }
+            RC_CK(cudaMalloc(&rc->d_pat_idx, (size_t) n_out * sizeof(int)));
+            RC_CK(cudaMalloc(&rc->d_pat_w, (size_t) n_out * sizeof(float)));
+            RC_CK(cudaMalloc(&rc->d_pattern, (size_t) rc->max_batch * np * sizeof(float2)));
+            RC_CK(cudaMemcpy(rc->d_pat_idx, idx.data(), (size_t) n_out * sizeof(int), cudaMemcpyHostToDevice));
+            RC_CK(cudaMemcpy(rc->d_pat_w, w.data(), (size_t) n_out * sizeof(float), cudaMemcpyHostToDevice));
+            rc->n_pat = np;
+        }
+        return 0;
+    });
+}
+
+// crop (+ fused corrections) of `batch` lines; `patterns`: host complex64 [batch][n_pat] or null
+static void rc_crop(I3B_RangeComp* rc, float2* d_out, int batch, int offset, const float* patterns, cudaStream_t s)
+{
+    const int n_out = rc->out_size, nfft = rc->fft_size;
+    const long long tout = (long long) batch * n_out;
+    const float2* d_pat = nullptr;
+    if (rc->n_pat > 0 && patterns) {
+        RC_CK(cudaMemcpyAsync(rc->d_pattern, patterns, (size_t) batch * rc->n_pat * sizeof(float2),
+                              cudaMemcpyHostToDevice, s));
+        d_pat = rc->d_pattern;
+    }
+    if (rc->d_col || d_pat)
+        rc_crop_scale_kernel<<<grid_for(tout), 256, 0, s>>>(d_out, rc->d_work, n_out, nfft, offset, tout, rc->d_col,
+                                                           rc->d_pat_idx, rc->d_pat_w, d_pat, rc->n_pat);
+    else
+        rc_crop_kernel<<<grid_for(tout), 256, 0, s>>>(d_out, rc->d_work, n_out, nfft, offset, tout);
+}
+
 int i3b_rangecomp_execute(I3B_RangeComp* rc, float* out, const float* in, int batch, uint32_t flags)
+{
+    return i3b_rangecomp_execute_scaled(rc, out, in, batch, flags, nullptr);
+}
+
+int i3b_rangecomp_execute_scaled(I3B_RangeComp* rc, float* out, const float* in, int batch, uint32_t flags,
+                                 const float* patterns)
 {
     return rc_guarded([&]() {
         if (!rc || !out || !in) throw RcError(I3B_EXC_INVALID_ARGUMENT, "null argument");
@@ -256,8 +375,7 @@ int i3b_rangecomp_execute(I3B_RangeComp* rc, float* out, const float* in, int ba
         const int offset = rc->mode == I3B_RANGECOMP_FULL ? 0
                            : rc->mode == I3B_RANGECOMP_VALID ? rc->chirp_size - 1 : rc->chirp_size / 2;
         // NOTE Valid mode with chirp longer than input: offset follows the reference literally
-        const long long tout = (long long) batch * n_out;
-        rc_crop_kernel<<<grid_for(tout), 256, 0, s>>>(d_out, rc->d_work, n_out, nfft, offset, tout);
+        rc_crop(rc, d_out, batch, offset, patterns, s);
         RC_CK(cudaGetLastError());
         RC_CK(cudaEventRecord(e1, s));
         if (!dev)
@@ -273,6 +391,12 @@ int i3b_rangecomp_execute(I3B_RangeComp* rc, float* out, const float* in, int ba
 }
 
 int i3b_rangecomp_execute_to_device(I3B_RangeComp* rc, const float* in, int64_t lines, float** dev_out)
+{
+    return i3b_rangecomp_execute_to_device_scaled(rc, in, lines, nullptr, dev_out);
+}
+
+int i3b_rangecomp_execute_to_device_scaled(I3B_RangeComp* rc, const float* in, int64_t lines,
+                                           const float* patterns, float** dev_out)
 {
     return rc_guarded([&]() {
         if (!rc || !in || !dev_out) throw RcError(I3B_EXC_INVALID_ARGUMENT, "null argument");
@@ -295,14 +419,14 @@ int i3b_rangecomp_execute_to_device(I3B_RangeComp* rc, const float* in, int64_t 
                 RC_CK(cudaMemcpyAsync(rc->d_in, in + 2 * (size_t) l0 * n_in, (size_t) batch * n_in * sizeof(float2),
                                       cudaMemcpyHostToDevice, s));
                 RC_CK(cudaEventRecord(e0, s));
-                const long long tot = (long long) batch * nfft, tout = (long long) batch * n_out;
+                const long long tot = (long long) batch * nfft;
                 rc_pad_kernel<<<grid_for(tot), 256, 0, s>>>(rc->d_work, rc->d_in, n_in, nfft, tot);
                 cufftHandle plan = rc->plan_for(batch);
                 RC_FFT(cufftExecC2C(plan, rc->d_work, rc->d_work, CUFFT_FORWARD));
                 rc_multiply_kernel<<<grid_for(tot), 256, 0, s>>>(rc->d_work, rc->d_ref, nfft, tot);
                 RC_FFT(cufftExecC2C(plan, rc->d_work, rc->d_work, CUFFT_INVERSE));
-                rc_crop_kernel<<<grid_for(tout), 256, 0, s>>>(d_all + (size_t) l0 * n_out, rc->d_work, n_out, nfft,
-                                                            offset, tout);
+                rc_crop(rc, d_all + (size_t) l0 * n_out, batch, offset,
+                        patterns ? patterns + 2 * (size_t) l0 * rc->n_pat : nullptr, s);
                 RC_CK(cudaGetLastError());
                 RC_CK(cudaEventRecord(e1, s));
                 RC_CK(cudaStreamSynchronize(s)); // d_in is reused by the next chunk

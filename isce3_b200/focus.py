@@ -425,7 +425,47 @@ class RangeComp:
     output_size = property(lambda self: self._output_size)
     first_valid_sample = property(lambda self: self._first)
 
-    def rangecompress(self, out, in_):
+    def set_scaling(self, column_scale=None, slant_ranges=None, pattern_ranges=None):
+        """Radiometric corrections fused into the pass that writes the output (extension): what
+        the workflow applies to every range-compressed block on the host
+        (nisar/workflows/focus.py:1956-1975).  ``column_scale`` (complex per output sample): the
+        per-column factors multiplied together -- baseband-shift phasors ``deramp_rc`` and range
+        loss ``slant_ranges / ref_range``.  ``slant_ranges`` + ``pattern_ranges``: enable the
+        per-line antenna-pattern division; ``rangecompress(..., patterns=P)`` then divides line b
+        by ``numpy.interp(slant_ranges, pattern_ranges, P[b])``.  No arguments: clear."""
+        self._scaling_keep = []
+        self._n_pattern = 0
+        if column_scale is None and pattern_ranges is None:
+            self._check(self._lib.i3b_rangecomp_set_scaling(self._handle, None))
+            return
+        sc = _capi.RangeCompScaling()
+        if column_scale is not None:
+            col = np.ascontiguousarray(column_scale, dtype=np.complex64)
+            if col.shape != (self._output_size,):
+                raise ValueError("column_scale length must equal output_size")
+            self._scaling_keep.append(col)
+            sc.column_scale = col.ctypes.data
+        if pattern_ranges is not None:
+            pr = np.ascontiguousarray(pattern_ranges, dtype=np.float64)
+            sr = np.ascontiguousarray(slant_ranges, dtype=np.float64)
+            if sr.shape != (self._output_size,):
+                raise ValueError("slant_ranges length must equal output_size")
+            self._scaling_keep += [pr, sr]
+            sc.slant_ranges, sc.pattern_ranges, sc.n_pattern = sr.ctypes.data, pr.ctypes.data, pr.size
+            self._n_pattern = pr.size
+        self._check(self._lib.i3b_rangecomp_set_scaling(self._handle, C.byref(sc)))
+
+    def _patterns(self, patterns, batch):
+        if patterns is None:
+            return None
+        if not getattr(self, "_n_pattern", 0):
+            raise ValueError("set_scaling(pattern_ranges=...) first")
+        pat = np.ascontiguousarray(patterns, dtype=np.complex64).reshape(batch, -1)
+        if pat.shape[1] != self._n_pattern:
+            raise ValueError("patterns must have one row of len(pattern_ranges) samples per line")
+        return pat
+
+    def rangecompress(self, out, in_, patterns=None):
         for a, name in ((out, "out"), (in_, "in")):
             if not isinstance(a, np.ndarray) or a.dtype != np.complex64 or not a.flags.c_contiguous:
                 raise TypeError(f"{name} must be a C-contiguous numpy array of complex64")
@@ -444,9 +484,11 @@ class RangeComp:
             raise ValueError("unexpected input length")
         if nout != self._output_size:
             raise ValueError("unexpected output length")
-        self._check(self._lib.i3b_rangecomp_execute(self._handle, out.ctypes.data, in_.ctypes.data, batch, 0))
+        pat = self._patterns(patterns, batch)
+        self._check(self._lib.i3b_rangecomp_execute_scaled(self._handle, out.ctypes.data, in_.ctypes.data, batch, 0,
+                                                           pat.ctypes.data if pat is not None else None))
 
-    def rangecompress_to_device(self, in_) -> "DeviceLines":
+    def rangecompress_to_device(self, in_, patterns=None) -> "DeviceLines":
         """Range-compress all lines of ``in_`` (2-D, any number of lines: chunks of ``maxbatch``)
         and leave the result in HBM (extension; see I3B_FLAG_DEVICE_INPUT)."""
         if not isinstance(in_, np.ndarray) or in_.dtype != np.complex64 or not in_.flags.c_contiguous:
@@ -456,8 +498,10 @@ class RangeComp:
         if in_.shape[1] != self._input_size:
             raise ValueError("unexpected input length")
         ptr = C.c_void_p()
-        self._check(self._lib.i3b_rangecomp_execute_to_device(self._handle, in_.ctypes.data, in_.shape[0],
-                                                              C.byref(ptr)))
+        pat = self._patterns(patterns, in_.shape[0])
+        self._check(self._lib.i3b_rangecomp_execute_to_device_scaled(
+            self._handle, in_.ctypes.data, in_.shape[0], pat.ctypes.data if pat is not None else None,
+            C.byref(ptr)))
         return DeviceLines(ptr.value, (in_.shape[0], self._output_size))
 
     def last_device_ms(self) -> float:

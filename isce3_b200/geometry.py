@@ -32,8 +32,6 @@ class DEMInterpolator:
         from .projections import make_projection
         make_projection(int(epsg))  # raises for codes createProj does not know
         self = cls(float(np.mean(data)) if ref_height is None else ref_height, method, epsg)
-        if self.interp_method == DataInterpMethod.SINC:
-            raise ValueError("sinc DEM interpolation is not supported on the TDBP path")
         self.data = data
         self.have_raster = True
         self.x_start, self.y_start = float(x_start), float(y_start)

@@ -12,6 +12,7 @@
 //   bicubic    cxx/isce3/core/BicubicInterpolator.cpp:35-62
 //   biquintic  cxx/isce3/core/Spline2dInterpolator.cpp:32-116 (order 6)
 //   nearest    cxx/isce3/core/NearestNeighborInterpolator.cpp:13-23
+//   sinc       cxx/isce3/core/Sinc2dInterpolator.cpp:13-133 (8 taps, 8192 sub-sample rows)
 //   LUT2d      cxx/isce3/core/LUT2d.cpp:127-160, LUT2d.h:84-95
 //   DEM        cxx/isce3/geometry/DEMInterpolator.cpp:592-659,
 //              cxx/isce3/core/Projections.h:127-133 (LonLat::forward)
@@ -22,6 +23,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <vector>
 
 #include "../include/isce3_b200_backproject.h"
 
@@ -134,6 +136,52 @@ inline U nearest(double x, double y, const Grid2d<U>& z)
     return z((long) std::round(y), (long) std::round(x));
 }
 
+// Sinc2dInterpolator.cpp: constructor :13-40 with _sinc_coef :116-133 (beta 1, pedestal 0,
+// weighted), as LUT2d / DEMInterpolator create it: createInterpolator(SINC_METHOD, 6, SINC_LEN = 8,
+// SINC_SUB = 8192) (LUT2d.cpp:184-188, Interpolator.h:205-217, Constants.h:32-35)
+inline const std::vector<double>& sinc_table()
+{
+    static const std::vector<double> table = [] {
+        const int len = 8, sub = 8192, n = len * sub;
+        std::vector<double> filter(n), t(n);
+        const double wgthgt = 0.5, soff = (n - 1.) / 2.;
+        for (int i = 0; i < n; ++i) {
+            const double wgt = (1. - wgthgt) + (wgthgt * std::cos((M_PI * (i - soff)) / soff));
+            const double s = std::floor(i - soff) / (1. * sub);
+            const double fct = (s != 0.) ? (std::sin(M_PI * s) / (M_PI * s)) : 1.;
+            filter[i] = fct * wgt;
+        }
+        for (int i = 0; i < sub; ++i) {
+            double ssum = 0.0;
+            for (int j = 0; j < len; ++j) ssum += filter[i + sub * j];
+            for (int j = 0; j < len; ++j) t[(size_t) i * len + j] = filter[i + sub * j] / ssum;
+        }
+        return t;
+    }();
+    return table;
+}
+
+// Sinc2dInterpolator.cpp:45-101 (interp_impl, _sinc_eval_2d)
+template<typename U>
+inline U sinc2d(double x, double y, const Grid2d<U>& z)
+{
+    const int len = 8, half = 4, sub = 8192;
+    const int ix = (int) std::floor(x), iy = (int) std::floor(y);
+    const double fx = x - ix, fy = y - iy;
+    if (ix < half - 1 || ix > z.cols - half - 1) return U(0);
+    if (iy < half - 1 || iy > z.rows - half - 1) return U(0);
+    const int xx = ix + half, yy = iy + half;
+    const int ifx = std::min(std::max(0, int(fx * sub)), sub - 1);
+    const int ify = std::min(std::max(0, int(fy * sub)), sub - 1);
+    const double* k = sinc_table().data();
+    U ret(0);
+    for (int i = 0; i < len; ++i)
+        for (int j = 0; j < len; ++j)
+            ret += z(yy - i, xx - j) * static_cast<U>(k[(size_t) ify * len + i]) *
+                   static_cast<U>(k[(size_t) ifx * len + j]);
+    return ret;
+}
+
 #ifdef TDBP_USE_REFERENCE_INTERPOLATORS
 } // namespace tdbp_oracle
 #include <isce3/core/Interpolator.h>
@@ -151,7 +199,9 @@ inline U interp2d(int method, double x, double y, const Grid2d<U>& z)
     static const isce3::core::BicubicInterpolator<U> bicubic_i;
     static const isce3::core::Spline2dInterpolator<U> biquintic_i(6);
     static const isce3::core::NearestNeighborInterpolator<U> nearest_i;
+    static const isce3::core::Sinc2dInterpolator<U> sinc_i(isce3::core::SINC_LEN, isce3::core::SINC_SUB);
     switch (method) {
+    case I3B_INTERP_SINC: return sinc_i.interpolate(x, y, m);
     case I3B_INTERP_BICUBIC: return bicubic_i.interpolate(x, y, m);
     case I3B_INTERP_BIQUINTIC: return biquintic_i.interpolate(x, y, m);
     case I3B_INTERP_NEAREST: return nearest_i.interpolate(x, y, m);
@@ -163,6 +213,7 @@ template<typename U>
 inline U interp2d(int method, double x, double y, const Grid2d<U>& z)
 {
     switch (method) {
+    case I3B_INTERP_SINC: return sinc2d<U>(x, y, z);
     case I3B_INTERP_BICUBIC: return bicubic<U>(x, y, z);
     case I3B_INTERP_BIQUINTIC: return biquintic<U>(x, y, z);
     case I3B_INTERP_NEAREST: return nearest<U>(x, y, z);

@@ -215,6 +215,22 @@ def test_biquintic_input_doppler_lut(oracle):
     check(run_gpu(sc), run_cpu(oracle, sc))
 
 
+def test_sinc_doppler_luts(oracle):
+    """2-D sinc interpolation (core/Sinc2dInterpolator.cpp: 8 x 8 taps from an 8192-row table)
+    of both Doppler LUTs; the reference returns 0 within half a kernel of a LUT's edges, so the
+    LUTs are large enough for the solutions to be interior (the root finder's probes still
+    visit the zero band, like on the CPU)."""
+    sc = synth.make_scene("c2", pulses=2048, bins=1024, out_lines=16, out_samples=160, n_targets=1)
+    sc.in_geometry = RadarGeometry(sc.in_geometry.radar_grid, sc.in_geometry.orbit,
+                                   _doppler_lut(sc.in_geometry, "sinc", -60.0, 90.0, shape=(24, 24)))
+    sc.out_geometry = RadarGeometry(sc.out_geometry.radar_grid, sc.out_geometry.orbit,
+                                    _doppler_lut(sc.out_geometry, "sinc", 40.0, -25.0, shape=(24, 24)))
+    gpu = run_gpu(sc)
+    cpu = run_cpu(oracle, sc)
+    check(gpu, cpu)
+    assert np.isfinite(gpu[1]).any()
+
+
 def test_lut_bounds_error_is_reported_and_lookups_are_clamped(oracle):
     """LUT2d(bounds_error=True) that does not cover the output swath: the CPU reference raises
     through its error channel (LUT2d.cpp:143-150), the reference CUDA path silently returns
@@ -269,7 +285,7 @@ def test_raster_dem_in_projected_coordinates(oracle, dem_epsg):
     check(gpu, cpu, sc)
 
 
-@pytest.mark.parametrize("method", ["bilinear", "bicubic", "nearest"])
+@pytest.mark.parametrize("method", ["bilinear", "bicubic", "nearest", "sinc"])
 def test_other_dem_interpolators(oracle, method):
     sc = synth.make_scene("c4", pulses=512, bins=1024, out_lines=8, out_samples=64, n_targets=1)
     sc.dem.interp_method = core.parse_interp_method(method)

@@ -176,3 +176,51 @@ def test_gpu_range_compressed_swath_stays_in_hbm_for_backprojection(oracle):
     tg = sc.targets[0]
     assert np.unravel_index(np.argmax(np.abs(out_dev)), shape) == (int(tg.az_index), int(tg.rg_index))
     dev.free()
+
+
+@gpu
+def test_gpu_fused_radiometric_corrections_match_the_workflow_host_pass():
+    """set_scaling / patterns: the workflow's host pass over every range-compressed block
+    (nisar/workflows/focus.py:1956-1975) -- ``*= deramp_rc[None, :]``, per line
+    ``/= np.interp(slant_ranges, pat_ranges, patterns[pulse])``, ``*= slant_ranges / ref_range``
+    -- fused into the kernel that writes the output."""
+    from isce3_b200.focus import RangeComp
+    rng = np.random.default_rng(21)
+    nchirp, ndata, batch = 257, 4000, 9
+    chirp = np.exp(1j * np.pi * 0.3 * (np.arange(nchirp) - nchirp / 2) ** 2 / nchirp).astype(np.complex64)
+    x = (rng.standard_normal((batch, ndata)) + 1j * rng.standard_normal((batch, ndata))).astype(np.complex64)
+    rc = RangeComp(chirp, ndata, maxbatch=4, mode=RangeComp.Mode.Valid)
+    n = rc.output_size
+    plain = np.zeros((4, n), np.complex64)
+    rc.rangecompress(plain, x[:4])
+    slant = 9.0e5 + 6.25 * np.arange(n)
+    deramp = np.exp(1j * 2 * np.pi * 0.013 * np.arange(n))
+    pat_ranges = np.linspace(slant[10], slant[-300], 40)  # does not cover the swath: clamped ends
+    patterns = ((1.0 + 0.3 * rng.uniform(size=(batch, 40))) *
+                np.exp(1j * 0.2 * rng.standard_normal((batch, 40)))).astype(np.complex64)
+    ref_range = slant[0]
+    want = plain.astype(np.complex128) * deramp[None, :]
+    for b in range(4):
+        want[b] /= np.interp(slant, pat_ranges, patterns[b])
+    want *= (slant / ref_range)[None, :]
+    rc.set_scaling(column_scale=deramp * slant / ref_range, slant_ranges=slant, pattern_ranges=pat_ranges)
+    got = np.zeros((4, n), np.complex64)
+    rc.rangecompress(got, x[:4], patterns=patterns[:4])
+    assert np.max(np.abs(got - want)) <= 2e-6 * np.max(np.abs(want))
+    # column factors only; and the resident route (chunks of maxbatch) with per-line patterns
+    rc.set_scaling(column_scale=deramp)
+    rc.rangecompress(got, x[:4])
+    assert np.max(np.abs(got - plain * deramp[None, :])) <= 2e-6 * np.max(np.abs(plain))
+    rc.set_scaling(column_scale=deramp * slant / ref_range, slant_ranges=slant, pattern_ranges=pat_ranges)
+    dev = rc.rangecompress_to_device(x, patterns=patterns)
+    full = dev.to_host()
+    dev.free()
+    rc.rangecompress(got, x[:4], patterns=patterns[:4])
+    np.testing.assert_array_equal(full[:4], got)
+    assert np.isfinite(full).all()
+    # cleared again: plain output
+    rc.set_scaling()
+    rc.rangecompress(got, x[:4])
+    np.testing.assert_array_equal(got, plain)
+    with pytest.raises(ValueError):
+        rc.rangecompress(got, x[:4], patterns=patterns[:4])
