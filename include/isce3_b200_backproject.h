@@ -14,11 +14,10 @@
  * i3b_last_error() returns the message of the last failure on this thread.
  *
  * All arrays are caller-owned, row-major, host memory (pageable is fine).  The
- * callee owns every device allocation and returns it before returning (one-shot
- * call) or at i3b_plan_destroy() (resident plan) -- to a per-process cache that
- * keeps it for the next call (a workflow calls backproject once per output
- * block); i3b_release_device_memory() gives the cached memory back to the
- * driver, I3B_POOL_KEEP_MB=<n> caps what is kept (0: nothing).
+ * callee owns every device allocation and frees it before returning (one-shot
+ * call) or at i3b_plan_destroy() / i3b_blocks_destroy() (resident objects).  A
+ * caller may opt in to a per-process cache that keeps freed buffers for the
+ * next call: i3b_set_device_memory_pool().
  */
 #ifndef ISCE3_B200_BACKPROJECT_H
 #define ISCE3_B200_BACKPROJECT_H
@@ -351,6 +350,13 @@ int i3b_device_count(void);
  * device once, focus.py:1592-1593).                                          */
 int i3b_current_device(void);
 int i3b_measure_peaks(int device, I3B_Peaks* peaks);
+/* Device memory between calls.  Default: none is kept -- every device allocation of a call is
+ * back with the driver when it returns (the reference's contract).  keep_mb < 0: keep freed
+ * buffers in a per-process cache for the next call, without limit (a workflow focusing block
+ * after block; avoids ~6 GB of cudaMalloc / cudaFree per call); keep_mb > 0: keep at most that
+ * many MiB; 0: back to the default (and release what is cached).  Environment variable
+ * I3B_POOL_KEEP_MB sets the initial value.                                           */
+int i3b_set_device_memory_pool(int64_t keep_mb);
 /* Return device memory cached by earlier calls to the driver (all devices). */
 int i3b_release_device_memory(void);
 /* Host-only diagnostic: the polynomial fit the fast kernel would use.      */

@@ -256,6 +256,7 @@ EXPORTED_SYMBOLS = (
     "i3b_measure_peaks",
     "i3b_fit_tap_polynomials",
     "i3b_release_device_memory",
+    "i3b_set_device_memory_pool",
     "i3b_blocks_create",
     "i3b_blocks_run",
     "i3b_blocks_destroy",
@@ -314,6 +315,8 @@ def load_library() -> C.CDLL:
     lib.i3b_fit_tap_polynomials.argtypes = [C.POINTER(Kernel), C.POINTER(TapPolyFit)]
     lib.i3b_fit_tap_polynomials.restype = C.c_int
     lib.i3b_release_device_memory.restype = C.c_int
+    lib.i3b_set_device_memory_pool.argtypes = [C.c_int64]
+    lib.i3b_set_device_memory_pool.restype = C.c_int
     lib.i3b_current_device.restype = C.c_int
     lib.i3b_blocks_create.argtypes = [C.POINTER(BackprojectArgs), C.POINTER(C.c_void_p)]
     lib.i3b_blocks_create.restype = C.c_int

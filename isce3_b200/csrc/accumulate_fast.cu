@@ -429,7 +429,6 @@ struct PairState {
 #ifndef I3B_SEG
 #define I3B_SEG 0
 #endif
-constexpr int SEG_MAX = 128; // pulses per geometry segment, at most (pulse-table padding)
 #ifndef I3B_SUB
 #define I3B_SUB 8
 #endif
@@ -1654,14 +1653,16 @@ int fast_tiles(int out_lines, int out_width)
 int fast_pulse_tile() { return TK; }
 // Segment length for a scene: the cubic through four exact phase values h = seg / prf apart
 // is off by at most 0.0234 h^4 |d4 phase / dt4|; for a platform at speed v passing a target at
-// range r that derivative is at most (4 pi / wavelength) 3 v^4 / r^3 (broadside; x4 for margin).
+// range r that derivative is (4 pi / wavelength) 3 v^4 / r^3 at closest approach, where it is
+// largest (x1.5 for margin).  128 pulses where that stays below 1.5e-6 rad (NISAR L-band:
+// 1.0e-6), else 64 (the airborne configuration: 2e-5 rad at 128, 1.3e-6 at 64).
 int fast_segment(double wavelength, double prf, double v_max, double r_min)
 {
     if (I3B_SEG) return I3B_SEG;
     if (!(wavelength > 0) || !(prf > 0) || !(v_max > 0) || !(r_min > 0)) return 64;
-    const double d4 = 4.0 * (4.0 * M_PI / wavelength) * 3.0 * std::pow(v_max, 4) / std::pow(r_min, 3);
+    const double d4 = 1.5 * (4.0 * M_PI / wavelength) * 3.0 * std::pow(v_max, 4) / std::pow(r_min, 3);
     const double h = 128.0 / prf;
-    return 0.0234 * std::pow(h, 4) * d4 <= 2e-6 ? 128 : 64;
+    return 0.0234 * std::pow(h, 4) * d4 <= 1.5e-6 ? 128 : 64;
 }
 
 void fast_tile_shape(int* tile_az, int* tile_rg)

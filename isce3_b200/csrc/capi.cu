@@ -48,13 +48,14 @@ struct ApiError : std::runtime_error {
 static thread_local std::string g_last_error;
 static thread_local I3B_Stats g_last_stats;
 
-// Device buffers are recycled through a small per-process cache instead of going back to the
-// driver after every call: a workflow calls backproject once per output block
-// (focus.py:1988-2007) with the same sizes, and in a process that has enabled peer access
-// (NCCL, multi-GPU) every cudaMalloc/cudaFree has to map/unmap the allocation on all peers --
-// measured 850 ms per call for this path's ~6 GB at 2 GPUs.  Buffers are returned to the cache
-// only after the streams that used them have been synchronised.  i3b_release_device_memory()
-// hands the cached memory back; I3B_POOL_KEEP_MB caps what is kept (0 = keep nothing).
+// Device buffers go through a per-process cache.  By DEFAULT it keeps nothing: every allocation
+// is back with the driver when a call returns, as the reference's ownership contract says
+// (Backproject.cu:691-695).  A caller that focuses block after block (focus.py:1988-2007) opts
+// in to keeping them -- i3b_set_device_memory_pool(-1) or I3B_POOL_KEEP_MB=-1 -- and saves the
+// cudaMalloc / cudaFree of ~6 GB per call; in a process that has enabled peer access (NCCL,
+// multi-GPU) each of those maps / unmaps the allocation on all peers: 850 ms per call measured
+// at 2 GPUs.  Buffers are returned to the cache only after the streams that used them have
+// been synchronised; i3b_release_device_memory() hands the cached memory back at any time.
 class DeviceCache {
 public:
     void* get(size_t bytes)
@@ -137,10 +138,28 @@ private:
         int device;
     };
     static constexpr size_t kGranule = (size_t) 2 << 20;
+
+public:
+    // bytes the cache may hold between calls: 0 (the default, like the reference: everything goes
+    // back to the driver before a call returns) unless the caller opted in through
+    // i3b_set_device_memory_pool() or I3B_POOL_KEEP_MB (MiB; negative: unlimited)
+    static std::atomic<long long>& limit_setting()
+    {
+        static std::atomic<long long> v {[] {
+            if (const char* e = std::getenv("I3B_POOL_KEEP_MB")) {
+                const long long mb = std::strtoll(e, nullptr, 10);
+                return mb < 0 ? -1LL : mb << 20;
+            }
+            return 0LL;
+        }()};
+        return v;
+    }
+
+private:
     static size_t keep_limit()
     {
-        if (const char* e = std::getenv("I3B_POOL_KEEP_MB")) return (size_t) std::strtoull(e, nullptr, 10) << 20;
-        return ~(size_t) 0 >> 1;
+        const long long v = limit_setting().load();
+        return v < 0 ? (~(size_t) 0 >> 1) : (size_t) v;
     }
     std::mutex mtx_;
     std::vector<Block> free_, live_;
@@ -1661,6 +1680,13 @@ int i3b_measure_peaks(int device, I3B_Peaks* peaks)
         if (rc != 0) CK((cudaError_t) rc);
         return 0;
     });
+}
+
+int i3b_set_device_memory_pool(int64_t keep_mb)
+{
+    DeviceCache::limit_setting().store(keep_mb < 0 ? -1LL : (long long) keep_mb << 20);
+    if (keep_mb == 0) device_cache().release_all();
+    return 0;
 }
 
 int i3b_release_device_memory(void)

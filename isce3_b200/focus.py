@@ -350,6 +350,12 @@ class BlockFocuser:
             pass
 
 
+def keep_device_memory(limit_mb=-1) -> None:
+    """Opt in to the per-process cache of device buffers (default: every call returns its device
+    memory to the driver, like the reference).  ``limit_mb`` < 0: unlimited, 0: off."""
+    _capi.load_library().i3b_set_device_memory_pool(int(limit_mb))
+
+
 def release_device_memory() -> None:
     """Hand the device memory cached by earlier calls back to the driver."""
     _capi.load_library().i3b_release_device_memory()

@@ -44,3 +44,13 @@ def oracles():
 def oracle(oracles):
     port, ref = oracles
     return ref if ref is not None else port
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _device_buffer_cache():
+    """The GPU tests opt in to the library's device-buffer cache (hundreds of small calls);
+    the default -- everything freed before a call returns -- has its own test."""
+    if _have_gpu():
+        from isce3_b200.focus import keep_device_memory
+        keep_device_memory(-1)
+    yield

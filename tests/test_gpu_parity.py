@@ -808,3 +808,41 @@ def test_compiled_pybind11_binding_gives_the_same_image(oracle):
     sc.rdr2geo_params = {"look_min": 0.0, "look_max": 0.3}
     assert isce.cuda.focus.backproject(out, *sc.backproject_args()) is True
     assert np.isnan(out).all()
+
+
+def test_device_memory_is_returned_by_default_and_kept_on_request():
+    """Ownership contract of the reference (all device memory freed before return,
+    cuda/focus/Backproject.cu:691-695) is the DEFAULT; the buffer cache is opt-in."""
+    import ctypes
+    from isce3_b200 import _capi
+    from isce3_b200.focus import keep_device_memory, release_device_memory
+    rt = None
+    for name in ("libcudart.so", "libcudart.so.12"):
+        try:
+            rt = ctypes.CDLL(name)
+            break
+        except OSError:
+            continue
+    if rt is None:
+        pytest.skip("no libcudart to query free memory with")
+
+    def free_bytes():
+        f, t = ctypes.c_size_t(), ctypes.c_size_t()
+        assert rt.cudaMemGetInfo(ctypes.byref(f), ctypes.byref(t)) == 0
+        return f.value
+    sc = synth.make_scene("c2", pulses=2048, bins=2048, out_lines=512, out_samples=1024, n_targets=1)
+    keep_device_memory(0)
+    release_device_memory()
+    run_gpu(sc)
+    base = free_bytes()
+    run_gpu(sc)
+    assert abs(free_bytes() - base) < (8 << 20)  # nothing of the call stays allocated
+    try:
+        keep_device_memory(-1)
+        run_gpu(sc)
+        kept = base - free_bytes()
+        assert kept > (30 << 20)  # per-pixel tables + swath stay cached for the next call
+        release_device_memory()
+        assert abs(free_bytes() - base) < (8 << 20)
+    finally:
+        keep_device_memory(0)
