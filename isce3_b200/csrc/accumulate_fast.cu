@@ -174,6 +174,7 @@ struct FastParams {
     int k_landed;   // pulses below this index are on the device (0: no such limit)
     int seg;        // pulses per geometry segment (a power of two, multiple of TK)
     double G;       // samples per cycle: 1 / (fc * dtau)
+    float Gf, Grf;  // (float) G and (float) (G / 2 pi): samples per turn / per radian of carrier phase
     double U0;      // swst / dtau
     double fc;
     int zero;       // always 0 (opaque to the compiler, see Weights::load_top)
@@ -869,6 +870,25 @@ __device__ __forceinline__ void subtile_steady(PairState& S, f32x2 A0, f32x2 A1,
     }
 }
 
+template<int V>
+struct NonUniformTag {
+    static constexpr int value = V;
+};
+// run loop: carry the run's position / staged-row address across runs; separate instance of the
+// loop for non-uniform pulse trains
+#ifndef I3B_RUN_CARRY
+#define I3B_RUN_CARRY 1
+#endif
+#ifndef I3B_NU_SPLIT
+#define I3B_NU_SPLIT 0 // (measured: the second instance of the loop costs 2 % -- instruction cache)
+#endif
+// interior runs that are not steady through the out-of-line per-pulse body: measured slower
+// (0.734 against 0.744 at 9 taps, 0.52 against 0.58 on the airborne frame, where a third of the
+// runs cross a sample boundary) -- the call moves the pair state through memory
+#ifndef I3B_NONSTEADY_CALL
+#define I3B_NONSTEADY_CALL 0
+#endif
+
 template<int K, int D, class Coef>
 __global__ void __launch_bounds__(NTHREADS, 2)
 accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, const __grid_constant__ PolyTable poly,
@@ -1079,8 +1099,8 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, const __grid_
     const uint32_t row_bytes = (uint32_t) P.W * (uint32_t) sizeof(float2);
     const unsigned jmax = (unsigned) (P.W - (K + 3));
     const double TWO_PI_D = 6.283185307179586476925;
-    const float Gr = (float) (P.G / TWO_PI_D); // samples per radian of carrier phase
-    const float Gsamp = (float) P.G;           // samples per cycle (turn) of carrier phase
+    const float Gr = P.Grf;   // samples per radian of carrier phase
+    const float Gsamp = P.Gf; // samples per cycle (turn) of carrier phase
     int seg_b = 0;                              // first pulse of the current segment
 
     for (int n = 0; n < ntiles; ++n) {
@@ -1166,18 +1186,43 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, const __grid_
         // run if the window position provably does not move, else per-pulse rounding; runs that
         // straddle an aperture edge -> the out-of-line edge path (skips pulses outside).
         const int iw0 = S.i0rel[0] - wlo, iw1 = S.i0rel[1] - wlo;
+        // position of each run's first pulse on the segment axis: the pulse index, or (non-uniform
+        // pulse trains) the time in nominal pulse intervals.  Carried across the runs of the tile
+        // together with the staged-row address, so a run starts from registers.
+        // (NU: non-uniform pulse train -- positions come from the xi table and no run is steady;
+        // the uniform instance of the loop never looks at the table)
+        auto run_tile = [&](auto nu_tag) {
+        constexpr int NUV = decltype(nu_tag)::value; // 1: non-uniform, 0: uniform, -1: decided per run
+        constexpr bool NU = NUV == 1;
+#if I3B_RUN_CARRY
+        float js = (float) (kt - seg_b);
+        uint32_t la = lines_addr;
+        int kr = kt; // first pulse of the run
+#pragma unroll 1
+        for (int sub = 0; sub < TK / SUB; ++sub, kr += SUB, js += (float) SUB, la += (uint32_t) SUB * row_bytes) {
+            asm volatile("" : "+r"(la), "+f"(js));
+#else
 #pragma unroll 1
         for (int sub = 0; sub < TK / SUB; ++sub) {
-            const int kr = kt + sub * SUB; // first pulse of the run
-            // position of the run's first pulse on the segment axis (pulse index, or time in
-            // nominal pulse intervals for non-uniform pulse trains)
-            const float js = P.xi ? __ldg(P.xi + kr) : (float) (kr - seg_b);
+            const int kr = kt + sub * SUB;
+            float js = (float) (kr - seg_b);
             const uint32_t la = lines_addr + (uint32_t) (sub * SUB) * row_bytes;
+#endif
+            const float* xi_run = nullptr;
+            if constexpr (NUV == 1) {
+                xi_run = P.xi + kr;
+                js = __ldg(xi_run);
+            } else if constexpr (NUV == -1) {
+                if (P.xi) {
+                    xi_run = P.xi + kr;
+                    js = __ldg(xi_run);
+                }
+            }
             RunPoly R = make_run_poly(S, js, Gsamp);
             if (I3B_EDGE_SPLIT && kr >= ks_max && kr + SUB <= ke_min) {
                 bool steady = false;
                 // (32 taps: the rolled steady loop gains nothing over the per-pulse path, measured)
-                if constexpr (I3B_STEADY && K < I3B_STEADY_MAX_TAPS) {
+                if constexpr (!NU && I3B_STEADY && K < I3B_STEADY_MAX_TAPS) {
                     const f32x2 Gr2 = bcast2(Gr);
                     // coordinate (minus floor(base) + 1/2) at the first and the last pulse of the run
                     const f32x2 XE = bcast2((float) (SUB - 1));
@@ -1211,9 +1256,21 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, const __grid_
                             subtile_steady<K, D, Coef, 0, SUB>(S, R.A0, A1, A2, R.A3, fbase, Gr, src, row_bytes, P.zero, poly_addr);
                     }
                 }
-                if (!steady)
-                    tile_body<K, D, Coef, false, SUB>(S, R, js, jjmax, la, row_bytes, wlo, jmax, Gr, 0u, 0u, P.zero, poly_addr,
-                                                      P.xi ? P.xi + kr : nullptr);
+                if (!steady) {
+                    if constexpr (I3B_NONSTEADY_CALL && !NU && I3B_STEADY && K < I3B_STEADY_MAX_TAPS) {
+                        // a few percent of the runs: through the out-of-line per-pulse body (every
+                        // pulse inside both apertures), which keeps ~900 instructions out of the
+                        // address range the steady runs loop over
+                        PairState T = S;
+                        jjmax = tile_body_edge<K, D, Coef>(T, R, js, jjmax, la, row_bytes, wlo, jmax, Gr, 0u, 0u, P.zero,
+                                                           poly_addr, xi_run, 0x7fffffffu, 0x7fffffffu);
+                        S.accp[0] = T.accp[0]; S.accp[1] = T.accp[1];
+                        S.accq[0] = T.accq[0]; S.accq[1] = T.accq[1];
+                    } else {
+                        tile_body<K, D, Coef, false, SUB>(S, R, js, jjmax, la, row_bytes, wlo, jmax, Gr, 0u, 0u, P.zero, poly_addr,
+                                                          xi_run);
+                    }
+                }
             } else {
                 // aperture of each pixel within this launch (re-read: edge runs are a few per
                 // pixel, their bounds do not deserve registers in the interior loops) and
@@ -1231,11 +1288,18 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, const __grid_
                 // interior paths should not find their pair state there)
                 PairState T = S;
                 jjmax = tile_body_edge<K, D, Coef>(T, R, js, jjmax, la, row_bytes, wlo, jmax, Gr, krel0, krel1, P.zero, poly_addr,
-                                                   P.xi ? P.xi + kr : nullptr, kspan[0], kspan[1]);
+                                                   xi_run, kspan[0], kspan[1]);
                 S.accp[0] = T.accp[0]; S.accp[1] = T.accp[1];
                 S.accq[0] = T.accq[0]; S.accq[1] = T.accq[1];
             }
         }
+        };
+#if I3B_NU_SPLIT
+        if (P.xi) run_tile(NonUniformTag<1>{});
+        else run_tile(NonUniformTag<0>{});
+#else
+        run_tile(NonUniformTag<-1>{});
+#endif
 
         // pulse tile done: fold FP32 partials into FP64, release the stage.
         // sum s*e^{j phi} = (P.x - Q.y) + j (P.y + Q.x)
@@ -1612,6 +1676,8 @@ int launch_accumulate_fast(const AccumParams& P, const DevKernel& hk, const Pixe
     FP.k_landed = P.k_landed;
     FP.seg = P.seg == 128 ? 128 : 64;
     FP.G = 1.0 / (P.fc * P.dtau);
+    FP.Gf = (float) FP.G;
+    FP.Grf = (float) (FP.G / 6.283185307179586476925);
     FP.U0 = P.swst / P.dtau;
     FP.fc = P.fc;
     FP.zero = 0;
