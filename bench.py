@@ -208,7 +208,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -653,7 +653,7 @@ def run_ours(args):
         # difference to ms_per_step (wall, barrier to barrier) is finalisation + host overhead
         "device_ms_per_step": kernel_ms_step + m["solve_ms_step"],
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     comm.close()
     return 0
 
@@ -719,9 +719,28 @@ def main():
                     help="main workload only: no other configs, pageable / in-library / generic arms")
     args = ap.parse_args()
     args.warmup_ref = min(args.warmup, 1)
+    # stdout carries ONE line, the JSON result: anything a library prints there while the bench
+    # runs (NCCL announces its version on stdout at communicator creation) goes to stderr
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)
+
+
+_RESULT_FD = None
+
+
+def emit(line: dict):
+    """The bench's one line of output, on the process's original stdout."""
+    text = json.dumps(line) + "\n"
+    if _RESULT_FD is None:
+        sys.stdout.write(text)
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, text.encode())
 
 
 if __name__ == "__main__":

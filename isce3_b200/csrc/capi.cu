@@ -386,15 +386,17 @@ struct Shard {
     int line0 = 0, nlines = 0;
     // declared before the buffers (destroyed after them)
     struct Streams {
-        cudaStream_t compute = nullptr, copy = nullptr;
+        cudaStream_t compute = nullptr, copy = nullptr, down = nullptr;
         ~Streams()
         {
             if (compute) cudaStreamDestroy(compute);
             if (copy) cudaStreamDestroy(copy);
+            if (down) cudaStreamDestroy(down);
         }
     } streams;
     cudaStream_t& compute = streams.compute;
     cudaStream_t& copy = streams.copy;
+    cudaStream_t& down = streams.down; // early device-to-host copies of the one-shot call
     DevBuf<double> out_pos, out_vel, in_pos, in_vel, out_dop, in_dop, pv, times, tn, sinc;
     DevBuf<float> xi;
     DevBuf<float> dem, kdata, height;
@@ -423,6 +425,14 @@ struct Shard {
     const PulseRec* pulse_shared = nullptr;
     const double* pv_shared = nullptr;
     const float2* range_cor_view = nullptr; // per-column output phasors of this shard's columns
+    // One-shot call with page-locked result arrays: parts of the result leave the device while
+    // the accumulation is still running -- the height layer as soon as the target solve is in,
+    // the image rows of every launch but the last as soon as they are final.
+    float2* early_out = nullptr;   // this shard's slice of the caller's image (null: no early copies)
+    float* early_height = nullptr; // ... of the caller's height layer
+    int out_rows_sent = 0;         // image rows [0, out_rows_sent) are on their way to the host
+    bool height_sent = false;
+    std::unique_ptr<Event> ev_part;
 
     ~Shard()
     {
@@ -434,6 +444,7 @@ struct Shard {
         if (compute || copy) cudaSetDevice(device);
         if (compute) cudaStreamSynchronize(compute);
         if (copy) cudaStreamSynchronize(copy);
+        if (down) cudaStreamSynchronize(down);
         if (cur >= 0) cudaSetDevice(cur);
     }
 };
@@ -462,6 +473,7 @@ static void shard_setup(const HostScene& hs, Shard& sh)
                                                   " is not sm_100-class; isce3_b200 has no fallback path");
     CK(cudaStreamCreateWithFlags(&sh.compute, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&sh.copy, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&sh.down, cudaStreamNonBlocking));
     cudaStream_t s = sh.compute;
     const I3B_RadarGeometry &og = a.out_geometry, &ig = a.in_geometry;
     sh.out_pos.upload(og.orbit.pos, 3 * (size_t) og.orbit.n, s);
@@ -833,6 +845,7 @@ static void shard_run(const HostScene& hs, Shard& sh, bool resident_only)
         int k_split = 0;     // rows >= rows_done have been integrated over pulses < k_split
         bool split_set = false;
         const int tile_az = sh.ap.tile_az;
+        int ramp = 8 * tk; // lines of the next slab while ramping up to `batch`
         // Launch policy once the solve is in.  Rows whose every pulse has landed get their whole
         // remaining aperture in one launch (row wavefront); while no row block is ready and the
         // GPU would idle -- the first rows need a full aperture on the device, most of the upload
@@ -853,6 +866,32 @@ static void shard_run(const HostScene& hs, Shard& sh, bool resident_only)
                 mark_start();
                 if (!landed.empty()) CK(cudaStreamWaitEvent(s, landed.back()->e, 0));
                 if (t_first < 0) t_first = since();
+                // The last launch in three parts (3/4, 3/16 and 1/16 of its rows): the image rows
+                // of a part are finalised and copied to the host while the next part is still
+                // being summed, which leaves a sixteenth of the image for after the last kernel.
+                if (sh.early_out) {
+                    const int total = sh.nlines - rows_done;
+                    for (int part = 0; part < 2; ++part) {
+                        const int upto = part == 0 ? total * 3 / 4 : total * 15 / 16;
+                        const int r_mid = sh.nlines - total + (upto / tile_az) * tile_az;
+                        if (r_mid - rows_done < 8 * tile_az || sh.nlines - r_mid < 4 * tile_az) continue;
+                        shard_accumulate(sh, k_split, klast, s, rows_done, r_mid, 0);
+                        const long long first = (long long) sh.out_rows_sent * sh.ap.out_width;
+                        const long long n = (long long) r_mid * sh.ap.out_width - first;
+                        launch_finalize(n, sh.ap.out_width, sh.pix.p + first, sh.acc.p + first, sh.out.p + first,
+                                        sh.range_cor_view, hs.a.mantissa_nbits, s);
+                        CK(cudaGetLastError());
+                        sh.stats.total_launches += 1;
+                        sh.ev_part.reset(new Event());
+                        sh.ev_part->record(s);
+                        CK(cudaStreamWaitEvent(sh.down, sh.ev_part->e, 0));
+                        CK(cudaMemcpyAsync(sh.early_out + first, sh.out.p + first, (size_t) n * sizeof(float2),
+                                           cudaMemcpyDeviceToHost, sh.down));
+                        sh.stats.d2h_bytes += (int64_t) n * (int64_t) sizeof(float2);
+                        sh.out_rows_sent = r_mid;
+                        rows_done = r_mid;
+                    }
+                }
                 shard_accumulate(sh, k_split, klast, s, rows_done, sh.nlines, 0);
                 rows_done = sh.nlines;
                 return;
@@ -883,6 +922,12 @@ static void shard_run(const HostScene& hs, Shard& sh, bool resident_only)
                 shard_solve_finish(sh); // (blocks only when every slab is already queued)
                 solved = true;
                 t_solved = since();
+                if (sh.early_height && sh.ap.npix > 0) {
+                    // the height layer is the solve's own output: final already
+                    CK(cudaMemcpyAsync(sh.early_height, sh.height.p, sh.height.n * sizeof(float), cudaMemcpyDeviceToHost, sh.down));
+                    sh.stats.d2h_bytes += (int64_t) (sh.height.n * sizeof(float));
+                    sh.height_sent = true;
+                }
                 kfirst = sh.stats.pulse_first;
                 klast = sh.stats.pulse_last;
                 fits = !(klast > kfirst && (kfirst < b0 || klast > b1));
@@ -890,7 +935,10 @@ static void shard_run(const HostScene& hs, Shard& sh, bool resident_only)
             }
             const int stop = solved ? std::max(std::min(klast, b1), b0) : b1;
             if (uploaded >= stop) break;
-            const int rows = std::min(slab, stop - uploaded);
+            // (the first slabs are short, so that the first launch does not wait for `batch`
+            // lines to cross a host link that several devices may be sharing)
+            const int rows = std::min(std::min(slab, ramp), stop - uploaded);
+            ramp = std::min(2 * ramp, std::max(slab, ramp));
             upload_slab(uploaded, rows);
             uploaded += rows;
             try_launch_rows(false);
@@ -960,7 +1008,10 @@ static void shard_run(const HostScene& hs, Shard& sh, bool resident_only)
     }
     const int kfirst = sh.stats.pulse_first, klast = sh.stats.pulse_last;
     if (sh.ap.npix > 0) {
-        launch_finalize(sh.ap.npix, sh.ap.out_width, sh.pix.p, sh.acc.p, sh.out.p, sh.range_cor_view, hs.a.mantissa_nbits, s);
+        // (rows [0, out_rows_sent) were finalised, and are being copied out, already)
+        const long long done = (long long) sh.out_rows_sent * sh.ap.out_width;
+        launch_finalize(sh.ap.npix - done, sh.ap.out_width, sh.pix.p + done, sh.acc.p + done, sh.out.p + done,
+                        sh.range_cor_view, hs.a.mantissa_nbits, s);
         CK(cudaGetLastError());
         sh.stats.total_launches += 1;
     }
@@ -982,6 +1033,10 @@ static void shard_run(const HostScene& hs, Shard& sh, bool resident_only)
         // kernel.  premature: a row-wavefront launch met a tile whose pulses had not all landed
         // (the host-side aperture bound failed) -> everything is on the device by now, again.
         if (redo_generic) sh.use_fast = false;
+        if (sh.out_rows_sent > 0) {
+            CK(cudaStreamSynchronize(sh.down)); // the rows copied out early are redone as well
+            sh.out_rows_sent = 0;
+        }
         DevStatus clr = st;
         clr.window_overflow = 0;
         clr.premature = 0;
@@ -998,6 +1053,18 @@ static void shard_run(const HostScene& hs, Shard& sh, bool resident_only)
     }
 }
 
+// Page-locked host memory (cudaHostAlloc / cudaHostRegister): an asynchronous copy into it
+// does not block the calling thread.
+static bool host_is_page_locked(const void* p)
+{
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return attr.type == cudaMemoryTypeHost;
+}
+
 static void shard_download(const HostScene& hs, Shard& sh, float* out, float* height)
 {
     CK(cudaSetDevice(sh.device));
@@ -1009,15 +1076,19 @@ static void shard_download(const HostScene& hs, Shard& sh, float* out, float* he
     Event e0, e1;
     e0.record(s);
     if (out && sh.ap.npix) {
-        CK(cudaMemcpyAsync(reinterpret_cast<float2*>(out) + off, sh.out.p, sh.out.n * sizeof(float2), kind, s));
-        sh.stats.d2h_bytes += (int64_t) (sh.out.n * sizeof(float2));
+        // (rows the one-shot call sent ahead are not copied again)
+        const size_t sent = sh.early_out ? (size_t) sh.out_rows_sent * width : 0;
+        CK(cudaMemcpyAsync(reinterpret_cast<float2*>(out) + off + sent, sh.out.p + sent,
+                           (sh.out.n - sent) * sizeof(float2), kind, s));
+        sh.stats.d2h_bytes += (int64_t) ((sh.out.n - sent) * sizeof(float2));
     }
-    if (height && sh.ap.npix) {
+    if (height && sh.ap.npix && !(sh.early_height && sh.height_sent)) {
         CK(cudaMemcpyAsync(height + off, sh.height.p, sh.height.n * sizeof(float), kind, s));
         sh.stats.d2h_bytes += (int64_t) (sh.height.n * sizeof(float));
     }
     e1.record(s);
     CK(cudaStreamSynchronize(s));
+    if (sh.down) CK(cudaStreamSynchronize(sh.down));
     sh.stats.ms_d2h = elapsed(e0, e1);
 }
 
@@ -1570,6 +1641,12 @@ int i3b_backproject(const I3B_BackprojectArgs* args)
             // starts doing so while the target solve is still running
             shard_solve_launch(plan->hs, sh);
             if (single) t_solve = lap();
+            if (!(args->flags & I3B_FLAG_DEVICE_POINTERS) && host_is_page_locked(out) &&
+                (!height || host_is_page_locked(height))) {
+                const size_t off = (size_t) sh.line0 * (size_t) args->out_geometry.grid.width;
+                sh.early_out = reinterpret_cast<float2*>(out) + off;
+                sh.early_height = height ? height + off : nullptr;
+            }
             shard_run(plan->hs, sh, false);
             if (single) t_run = lap();
             shard_download(plan->hs, sh, out, height);
