@@ -474,8 +474,29 @@ def run_ours(args):
                      "what": "rank 0 alone: backproject(out, ..., devices=[0..N-1]) on the whole frame, "
                              "ONE pageable input array, ONE pageable output array, one host thread per device",
                      "vs_torchrun_e2e": (s2["pixel_pulses"] / dt) / m["e2e"]["value"],
+                     "vs_torchrun_e2e_pageable": ((s2["pixel_pulses"] / dt) / e2e_pageable["value"]
+                                                  if e2e_pageable else None),
                      "rank0_block_bit_identical_to_torchrun": bool(np.array_equal(full[a0:a1], m["img"]))}
             del full
+            # the same single call from page-locked arrays (what the torchrun `e2e` arm uses)
+            try:
+                import torch
+                full_pin = torch.empty((og.grid_length, og.grid_width), dtype=torch.complex64, pin_memory=True).numpy()
+                pin_args = (og, rc_host) + common
+                backproject(full_pin, *pin_args, batch=args.batch, devices=devs)
+                t0 = time.perf_counter()
+                for _ in range(n_il):
+                    backproject(full_pin, *pin_args, batch=args.batch, devices=devs)
+                dtp = (time.perf_counter() - t0) / n_il
+                s3 = last_stats()
+                inlib["pinned"] = {"value": s3["pixel_pulses"] / dtp, "unit": UNIT, "ms_per_step": 1e3 * dtp,
+                                   "what": "the same single call with page-locked input and output arrays",
+                                   "vs_torchrun_e2e": (s3["pixel_pulses"] / dtp) / m["e2e"]["value"],
+                                   "rank0_block_bit_identical_to_torchrun":
+                                       bool(np.array_equal(full_pin[a0:a1], m["img"]))}
+                del full_pin
+            except Exception as exc:  # noqa: BLE001 -- an extra arm must not take the line down
+                inlib["pinned"] = {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
             release_device_memory()
         comm.host_barrier()
 

@@ -1168,6 +1168,11 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, const __grid_
                 f0[p] = (float) (uh - ufl) - 0.5f;
                 S.i0rel[p] = (int) ufl + LOWOFF - MAGIC32_BITS; // window origin added per tile
             }
+            // Guard on the phase rate: a run evaluates A0 + A1 x + ... with |A0| <= pi and x < SUB
+            // in FP32, good to ~6e-8 |A1| SUB rad.  Beyond 1e3 rad per run (a Doppler centroid of
+            // ~20 PRFs; nothing the workflow produces) the call is handed to the generic kernel
+            // through the same flag as a window overflow.
+            if (fmaxf(fabsf(c1[0]), fabsf(c1[1])) * (float) SUB > 1.0e3f) jjmax = 0xffffffffu;
             S.c1 = pack2(c1[0], c1[1]);
             S.c1l = pack2(c1lo[0], c1lo[1]);
             S.c2 = pack2(c2[0], c2[1]);
