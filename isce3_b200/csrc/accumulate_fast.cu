@@ -892,6 +892,14 @@ struct NonUniformTag {
 #ifndef I3B_NU_SPLIT
 #define I3B_NU_SPLIT 0 // (measured: the second instance of the loop costs 2 % -- instruction cache)
 #endif
+// I3B_PAIR_RUNS = 1: a steady run that stays steady over the whole 16-pulse tile is proven once
+// and the tile's second run reuses the (re-centred) phase quadratic, window and fraction base of
+// the first -- 60 instructions fewer per tile, and measured SLOWER (9 taps: 0.731 against 0.744
+// of FP32 peak; 8 taps airborne 0.54 against 0.58): the run set-up issues in the shadow of other
+// warps' FFMA2 work, what the chain adds is a longer dependent path into the second body.
+#ifndef I3B_PAIR_RUNS
+#define I3B_PAIR_RUNS 0
+#endif
 // interior runs that are not steady through the out-of-line per-pulse body: measured slower
 // (0.734 against 0.744 at 9 taps, 0.52 against 0.58 on the airborne frame, where a third of the
 // runs cross a sample boundary) -- the call moves the pair state through memory
@@ -1186,7 +1194,8 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, const __grid_
             const float curv1 = 2.f * fabsf(c2[1]) + (6.f * SEG) * fabsf(c3[1]);
             S.flim = 0.5f - 1e-5f - fabsf(Gr) * fmaxf(curv0, curv1) * ((SUB - 1) * (SUB - 1) / 8.0f);
             if (I3B_QUAD_RUN) {
-                constexpr float kDev = 0.0481125f * (SUB - 1) * (SUB - 1) * (SUB - 1);
+                constexpr int kSpan = I3B_PAIR_RUNS ? TK - 1 : SUB - 1; // longest span a quadratic covers
+                constexpr float kDev = 0.0481125f * kSpan * kSpan * kSpan;
                 if (fmaxf(fabsf(c3[0]), fabsf(c3[1])) * kDev > 2e-6f) S.flim = -1.0f;
             }
             if (P.xi) S.flim = -1.0f; // steady runs step the phase by whole pulse indices
@@ -1209,6 +1218,11 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, const __grid_
         auto run_tile = [&](auto nu_tag) {
         constexpr int NUV = decltype(nu_tag)::value; // 1: non-uniform, 0: uniform, -1: decided per run
         constexpr bool NU = NUV == 1;
+        // a steady run proven for the whole 16-pulse tile hands its quadratic to the second run
+        bool chain = false;
+        f32x2 cA0 = 0ull, cA1 = 0ull, cA2 = 0ull, cfb = 0ull;
+        uint32_t csrc = 0u;
+        unsigned cpar = 0u;
 #if I3B_RUN_CARRY
         float js = (float) (kt - seg_b);
         uint32_t la = lines_addr;
@@ -1233,45 +1247,96 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, const __grid_
                     js = __ldg(xi_run);
                 }
             }
-            RunPoly R = make_run_poly(S, js, Gsamp);
-            if (I3B_EDGE_SPLIT && kr >= ks_max && kr + SUB <= ke_min) {
-                bool steady = false;
+            // ---- what this run is: second half of a proven 16-pulse steady run (chained), steady,
+            // per-pulse, or aperture edge ----
+            RunPoly R{};
+            bool steady = false;
+            f32x2 sA0 = 0ull, sA1 = 0ull, sA2 = 0ull, sfb = 0ull; // steady run: phase quadratic, fraction base
+            uint32_t ssrc = 0u;                                   // ... first window address
+            unsigned spar = 0u;                                   // ... window parity
+            bool chain_next = false;
+            const bool interior = I3B_EDGE_SPLIT && kr >= ks_max && kr + SUB <= ke_min;
+            if (chain) {
+                steady = true;
+                sA0 = cA0, sA1 = cA1, sA2 = cA2, sfb = cfb, ssrc = csrc, spar = cpar;
+            } else {
+                R = make_run_poly(S, js, Gsamp);
                 // (32 taps: the rolled steady loop gains nothing over the per-pulse path, measured)
                 if constexpr (!NU && I3B_STEADY && K < I3B_STEADY_MAX_TAPS) {
-                    const f32x2 Gr2 = bcast2(Gr);
-                    // coordinate (minus floor(base) + 1/2) at the first and the last pulse of the run
-                    const f32x2 XE = bcast2((float) (SUB - 1));
-                    const f32x2 ange = fma2(fma2(fma2(R.A3, XE, R.A2), XE, R.A1), XE, R.A0);
-                    const f32x2 g0 = fma2(R.A0, Gr2, R.f0m), ge = fma2(ange, Gr2, R.f0m);
-                    const f32x2 mm = add2(g0, bcast2(MAGIC32));
-                    const f32x2 tt = add2(mm, bcast2(-MAGIC32)); // integer part at the first pulse
-                    const f32x2 fa = sub2(g0, tt), fe = sub2(ge, tt);
-                    float m0, m1, fa0, fa1, fe0, fe1;
-                    unpack2(mm, m0, m1);
-                    unpack2(fa, fa0, fa1);
-                    unpack2(fe, fe0, fe1);
-                    const unsigned jj0 = (unsigned) (iw0 + __float_as_int(m0));
-                    const unsigned jj1 = (unsigned) (iw1 + __float_as_int(m1));
-                    const float worst = fmaxf(fmaxf(fabsf(fa0), fabsf(fa1)), fmaxf(fabsf(fe0), fabsf(fe1)));
-                    // steady: same integer part over the whole run (both pixels), adjacent windows
-                    // inside the staged rows
-                    steady = worst <= S.flim && jj1 == jj0 + 1u && jj0 < jmax;
-                    if (steady) {
-                        const uint32_t src = la + ((jj0 >> 1) << 4);
-                        const f32x2 fbase = sub2(R.f0m, tt);
-                        f32x2 A1 = R.A1, A2 = R.A2;
-                        if (I3B_QUAD_RUN) {
-                            // quadratic through the cubic at x = 0, (SUB-1)/2, SUB-1
-                            A1 = fma2(R.A3, bcast2(-0.5f * (SUB - 1) * (SUB - 1)), A1);
-                            A2 = fma2(R.A3, bcast2(1.5f * (SUB - 1)), A2);
+                    if (interior) {
+                        const f32x2 Gr2 = bcast2(Gr);
+                        // coordinate (minus floor(base) + 1/2) at the first and the last pulse of the run
+                        const f32x2 XE = bcast2((float) (SUB - 1));
+                        const f32x2 ange = fma2(fma2(fma2(R.A3, XE, R.A2), XE, R.A1), XE, R.A0);
+                        const f32x2 g0 = fma2(R.A0, Gr2, R.f0m), ge = fma2(ange, Gr2, R.f0m);
+                        const f32x2 mm = add2(g0, bcast2(MAGIC32));
+                        const f32x2 tt = add2(mm, bcast2(-MAGIC32)); // integer part at the first pulse
+                        const f32x2 fa = sub2(g0, tt), fe = sub2(ge, tt);
+                        float m0, m1, fa0, fa1, fe0, fe1;
+                        unpack2(mm, m0, m1);
+                        unpack2(fa, fa0, fa1);
+                        unpack2(fe, fe0, fe1);
+                        const unsigned jj0 = (unsigned) (iw0 + __float_as_int(m0));
+                        const unsigned jj1 = (unsigned) (iw1 + __float_as_int(m1));
+                        const float worst0 = fmaxf(fabsf(fa0), fabsf(fa1));
+                        const float worst = fmaxf(worst0, fmaxf(fabsf(fe0), fabsf(fe1)));
+                        // steady: same integer part over the whole run (both pixels), adjacent windows
+                        // inside the staged rows
+                        const bool placed = jj1 == jj0 + 1u && jj0 < jmax;
+                        steady = worst <= S.flim && placed;
+                        if (steady) {
+                            ssrc = la + ((jj0 >> 1) << 4);
+                            spar = jj0 & 1u;
+                            sfb = sub2(R.f0m, tt);
+                            sA0 = R.A0, sA1 = R.A1, sA2 = R.A2;
+                            int span = SUB - 1; // the quadratic replaces the cubic over this many pulse steps
+                            if (I3B_PAIR_RUNS && TK == 2 * SUB && sub == 0 && kr + TK <= ke_min) {
+                                // Can the NEXT run ride along?  Same test over all 16 pulses of the
+                                // tile (the curvature allowance grows with the span squared): if it
+                                // holds, the second run needs no polynomial and no proof of its own.
+                                const f32x2 XT = bcast2((float) (TK - 1));
+                                const f32x2 angt = fma2(fma2(fma2(R.A3, XT, R.A2), XT, R.A1), XT, R.A0);
+                                const f32x2 ft = sub2(fma2(angt, Gr2, R.f0m), tt);
+                                float ft0, ft1;
+                                unpack2(ft, ft0, ft1);
+                                constexpr float kHalf = 0.5f - 1e-5f;
+                                constexpr float kGrow = (float) ((TK - 1) * (TK - 1)) / (float) ((SUB - 1) * (SUB - 1));
+                                const float flim_t = fmaf(kGrow, S.flim - kHalf, kHalf);
+                                if (fmaxf(worst0, fmaxf(fabsf(ft0), fabsf(ft1))) <= flim_t) {
+                                    chain_next = true;
+                                    span = TK - 1;
+                                }
+                            }
+                            if (I3B_QUAD_RUN) {
+                                // quadratic through the cubic at x = 0, span / 2, span
+                                const float n = (float) span;
+                                sA1 = fma2(R.A3, bcast2(-0.5f * n * n), sA1);
+                                sA2 = fma2(R.A3, bcast2(1.5f * n), sA2);
+                            }
                         }
-                        if (jj0 & 1u)
-                            subtile_steady<K, D, Coef, 1, SUB>(S, R.A0, A1, A2, R.A3, fbase, Gr, src, row_bytes, P.zero, poly_addr);
-                        else
-                            subtile_steady<K, D, Coef, 0, SUB>(S, R.A0, A1, A2, R.A3, fbase, Gr, src, row_bytes, P.zero, poly_addr);
                     }
                 }
-                if (!steady) {
+            }
+            if (steady) {
+                if (spar)
+                    subtile_steady<K, D, Coef, 1, SUB>(S, sA0, sA1, sA2, R.A3, sfb, Gr, ssrc, row_bytes, P.zero, poly_addr);
+                else
+                    subtile_steady<K, D, Coef, 0, SUB>(S, sA0, sA1, sA2, R.A3, sfb, Gr, ssrc, row_bytes, P.zero, poly_addr);
+                if (chain_next) {
+                    // re-centre the quadratic on the next run's first pulse; window, parity and
+                    // fraction base carry over
+                    const f32x2 X = bcast2((float) SUB);
+                    cA0 = fma2(fma2(sA2, X, sA1), X, sA0);
+                    cA1 = fma2(sA2, bcast2(2.0f * SUB), sA1);
+                    cA2 = sA2;
+                    cfb = sfb;
+                    csrc = ssrc + (uint32_t) SUB * row_bytes;
+                    cpar = spar;
+                }
+                chain = chain_next;
+            } else if (interior) {
+                chain = false;
+                {
                     if constexpr (I3B_NONSTEADY_CALL && !NU && I3B_STEADY && K < I3B_STEADY_MAX_TAPS) {
                         // a few percent of the runs: through the out-of-line per-pulse body (every
                         // pulse inside both apertures), which keeps ~900 instructions out of the
@@ -1287,6 +1352,7 @@ accumulate_fast_kernel(const __grid_constant__ CUtensorMap rc_map, const __grid_
                     }
                 }
             } else {
+                chain = false;
                 // aperture of each pixel within this launch (re-read: edge runs are a few per
                 // pixel, their bounds do not deserve registers in the interior loops) and
                 // k - kstart for the first pulse of the run
