@@ -124,6 +124,28 @@ def dist_env():
     return rank, world, local
 
 
+def bind_near_gpu(local):
+    """One rank per GPU: run this rank (and allocate its host buffers, first touch) on the CPUs of
+    the GPU's own NUMA node, as a multi-GPU launcher does (numactl / --cpu-bind).  Returns
+    (cpus bound to, cpus allowed before) or (None, allowed) when nothing could be learnt."""
+    allowed = os.sched_getaffinity(0)
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(local)
+        bus_id = f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus_id.encode())
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (max(allowed) + 64) // 64)
+        near = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1} & allowed
+        if near and near != allowed:
+            os.sched_setaffinity(0, near)
+            return sorted(near), allowed
+    except Exception:  # noqa: BLE001 -- binding is an optimisation, never a requirement
+        pass
+    return None, allowed
+
+
 def make_scene(config, scale=1.0, taps=0, **extra):
     from testkit import synth
     kw = dict(extra)
@@ -407,6 +429,7 @@ def run_ours(args):
         tdbp.set_threads(cores)  # torchrun exports OMP_NUM_THREADS=1 to its workers
         oracle = tdbp.best()
 
+    bound_cpus, all_cpus = bind_near_gpu(local) if world > 1 else (None, os.sched_getaffinity(0))
     t_gen = time.perf_counter()
     sc = make_scene(args.config, args.scale, args.taps)
     t_gen = time.perf_counter() - t_gen
@@ -457,6 +480,7 @@ def run_ours(args):
         release_device_memory()
         comm.host_barrier()
         if rank == 0:
+            os.sched_setaffinity(0, all_cpus)  # one process drives every device from here
             full = np.empty((og.grid_length, og.grid_width), np.complex64)
             devs = list(range(world))
             full_args = (og, sc.rc) + common
@@ -502,6 +526,7 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and oracle is not None:
+        os.sched_setaffinity(0, all_cpus)  # the CPU baseline uses every host core
         cpu, _ = cpu_parity(comm, sc, m, oracle, cores)
         # one-thread figure on a proportionally smaller sample
         from oracle import tdbp
@@ -512,6 +537,8 @@ def run_ours(args):
         cpu["value_1_thread"] = ppx * cols / dt1
         cpu["sample_1_thread"] = f"1 azimuth line x {cols} range pixels ({ppx * cols:.3g} pixel*pulses, {dt1:.1f} s)"
         tdbp.set_threads(cores)
+    if bound_cpus:
+        os.sched_setaffinity(0, set(bound_cpus))  # back next to the GPU for the remaining arms
 
     # ---- same-GPU comparator: the reference's own CUDA backprojection (reduced harness) ---
     ref_cuda = None
@@ -663,7 +690,10 @@ def run_ours(args):
                    "pixel_pulses_per_step": m["pp_total"], "batch": args.batch,
                    "device_memory": "per-process buffer cache enabled (i3b_set_device_memory_pool(-1); "
                                     "the library's default frees every device allocation before a call returns)",
-                   "scene_generation_s": t_gen},
+                   "scene_generation_s": t_gen,
+                   "cpu_binding": (f"each rank bound to the {len(bound_cpus)} CPUs of its GPU's NUMA node "
+                                   "(NVML cpu affinity) before its host buffers are allocated"
+                                   if bound_cpus else "none")},
         "e2e": m["e2e"], "e2e_pageable": e2e_pageable,
         "gpu_launches": int(m["launches"]),
         "clocks": m["clocks"], "roofline": roofline, "roofline_general": roofline_general,
