@@ -116,8 +116,19 @@ __device__ inline void orbit_legendre(const DevOrbit& o, double t, D3* pos, D3* 
 }
 
 // LEG = false: the caller knows (at compile time) that no orbit on its path is Legendre
+// I3B_OUTLINE_MORE = 1: the ellipsoid conversion and the orbit interpolation as real functions
+// too (see the note at the raster samplers)
+#ifndef I3B_OUTLINE_MORE
+#define I3B_OUTLINE_MORE 0
+#endif
+#if I3B_OUTLINE_MORE
+#define I3B_MAYBE_NOINLINE __noinline__
+#else
+#define I3B_MAYBE_NOINLINE
+#endif
+
 template<bool LEG = true>
-__device__ inline int orbit_interpolate(const DevOrbit& o, double t, int border, D3* pos, D3* vel)
+__device__ I3B_MAYBE_NOINLINE inline int orbit_interpolate(const DevOrbit& o, double t, int border, D3* pos, D3* vel)
 {
     const int method = LEG ? o.method : (int) I3B_ORBIT_HERMITE;
     const int need = method == I3B_ORBIT_LEGENDRE ? 9 : 4;
@@ -154,7 +165,7 @@ __device__ inline D3 llh_to_xyz(D3 llh)
 }
 
 // Vermeille (2002) closed form.
-__device__ inline D3 xyz_to_llh(D3 p3)
+__device__ I3B_MAYBE_NOINLINE inline D3 xyz_to_llh(D3 p3)
 {
     const double e4 = kE2 * kE2, a2 = kA * kA;
     const double rho2 = p3.x * p3.x + p3.y * p3.y;
@@ -362,6 +373,24 @@ __device__ inline U interp2d(int method, double x, double y, const G& z, const d
     }
 }
 
+// The 2-D samplers of a raster (five interpolation methods each, the spline and sinc ones
+// hundreds of instructions) are real functions: the solvers that call them from inside a
+// root finder were instruction-fetch bound with them inlined at every call site (raster-DEM
+// target solve: 38 k instructions, 14 warps stalled on "no instruction" per issue, ncu round 2).
+__device__ __noinline__ inline double lut_sample_outlined(const double* data, int length, int width, int method,
+                                                          double xi, double yi, const double* sinc)
+{
+    const Grid2d<double, true> g {data, length, width};
+    return interp2d<double, Grid2d<double, true>>(method, xi, yi, g, sinc);
+}
+
+__device__ __noinline__ inline double dem_sample_outlined(const float* data, int length, int width, int method,
+                                                          double col, double row, const double* sinc)
+{
+    const Grid2d<float> g {data, length, width};
+    return interp2d<float, Grid2d<float>>(method, col, row, g, sinc);
+}
+
 // LUT = false: the caller knows that no Doppler LUT on its path holds data
 template<bool LUT = true>
 __device__ inline double lut2d_eval(const DevLUT2d& l, double y, double x)
@@ -371,8 +400,7 @@ __device__ inline double lut2d_eval(const DevLUT2d& l, double y, double x)
     double yi = (y - l.ystart) / l.dy;
     xi = fmin(fmax(xi, 0.0), l.width - 1.0);
     yi = fmin(fmax(yi, 0.0), l.length - 1.0);
-    const Grid2d<double, true> g {l.data, l.length, l.width};
-    return interp2d<double, Grid2d<double, true>>(l.method, xi, yi, g, l.sinc);
+    return lut_sample_outlined(l.data, l.length, l.width, l.method, xi, yi, l.sinc);
 }
 
 // LUT2d::contains (core/LUT2d.h:84-95)
@@ -409,36 +437,59 @@ __device__ inline double dem_interp_lonlat(const DevDEM& d, double lon, double l
     const int irow = (int) floor(row), icol = (int) floor(col);
     if (irow < 2 || irow >= d.length - 1) return d.ref_height;
     if (icol < 2 || icol >= d.width - 1) return d.ref_height;
-    const Grid2d<float> g {d.data, d.length, d.width};
-    return interp2d<float, Grid2d<float>>(d.method, col, row, g, d.sinc);
+    return dem_sample_outlined(d.data, d.length, d.width, d.method, col, row, d.sinc);
 }
 
 // ---- Brent's bracketing root finder ---------------------------------------------
 
 __device__ inline bool opposite_sign(double a, double b) { return signbit(a) != signbit(b); }
 
+// (The function is evaluated at ONE place in the code -- the initial end-point evaluations and
+// the one per iteration share it -- so that a large `f`, inlined, appears once.  Arithmetic and
+// control flow are those of the reference's loop, math/detail/RootFind1dBracket.icc.)
 template<class F>
 __device__ inline int brent(double a, double b, F f, const double tol, double* root)
 {
     if (tol < 0.0) return I3B_INVALID_TOLERANCE;
-    double c, d, e, fa, fb, fc, p, q, r, s, tol1;
-    fa = f(a);
-    if (fa == 0.0) {
-        *root = a;
-        return I3B_SUCCESS;
-    }
-    fb = f(b);
-    if (fb == 0.0) {
-        *root = b;
-        return I3B_SUCCESS;
-    }
-    if (!opposite_sign(fa, fb)) return I3B_INVALID_INTERVAL;
-    c = a;
-    fc = fa;
-    e = d = b - a;
-    tol1 = tol > 0.0 ? tol : DBL_EPSILON;
-    const int maxiter = 3 * (int) ceil(log2(fabs((a - b) / tol1)));
-    for (int it = 0; it < maxiter; ++it) {
+    double c = 0.0, d = 0.0, e = 0.0, fa = 0.0, fb = 0.0, fc = 0.0, p, q, r, s, tol1;
+    int maxiter = 0, it = 0, stage = 0; // stage 0: f(a) pending, 1: f(b) pending, 2: iterating
+    double x = a;
+#pragma unroll 1
+    for (;;) {
+        const double fx = f(x);
+        if (stage == 0) {
+            fa = fx;
+            if (fa == 0.0) {
+                *root = a;
+                return I3B_SUCCESS;
+            }
+            stage = 1;
+            x = b;
+            continue;
+        }
+        if (stage == 1) {
+            fb = fx;
+            if (fb == 0.0) {
+                *root = b;
+                return I3B_SUCCESS;
+            }
+            if (!opposite_sign(fa, fb)) return I3B_INVALID_INTERVAL;
+            c = a;
+            fc = fa;
+            e = d = b - a;
+            tol1 = tol > 0.0 ? tol : DBL_EPSILON;
+            maxiter = 3 * (int) ceil(log2(fabs((a - b) / tol1)));
+            stage = 2;
+        } else {
+            fb = fx;
+            if (!opposite_sign(fb, fc)) {
+                c = a;
+                fc = fa;
+                e = d = b - a;
+            }
+            ++it;
+        }
+        if (it >= maxiter) break;
         if (fabs(fc) < fabs(fb)) {
             a = b; b = c; c = a;
             fa = fb; fb = fc; fc = fa;
@@ -475,12 +526,7 @@ __device__ inline int brent(double a, double b, F f, const double tol, double* r
         fa = fb;
         if (fabs(d) <= tol1) b = (xm <= 0.0) ? b - tol1 : b + tol1;
         else b = b + d;
-        fb = f(b);
-        if (!opposite_sign(fb, fc)) {
-            c = a;
-            fc = fa;
-            e = d = b - a;
-        }
+        x = b;
     }
     *root = b;
     return I3B_FAILED_TO_CONVERGE;
@@ -563,6 +609,10 @@ __device__ inline int rdr2geo_bracket(double aztime, double slant_range, double 
         const D3 llh = xyz_to_llh(get_xyz(look_));
         return llh.z - dem_interp_lonlat(dem, llh.x, llh.y);
     };
+    // (A narrower bracket was tried for rasters -- the look angles at which the circle crosses
+    // the raster's height range, licensed by a measured gradient bound that rules out layover:
+    // Brent needs ~8 evaluations from the full interval and the bracket's own set-up costs as
+    // much as it saves; 41.8 ms against 33.9 ms on the C4 frame.  The reference's interval it is.)
     const int err = brent(prm.look_min, prm.look_max, dh, tol_look, &look);
     if (err != I3B_SUCCESS) return err;
     *xyz = get_xyz(look);
@@ -603,18 +653,35 @@ __device__ inline int geo2rdr_bracket(D3 x, const DevOrbit& orbit, const DevLUT2
         // stops at -- for two evaluations instead of a search.
         const double hw = 0.5 * prm.tol_aztime;
         if (hw > 0.0 && t_guess - hw >= t0 && t_guess + hw <= t1) {
-            const double fa = doppler_error(t_guess - hw), fb = doppler_error(t_guess + hw);
-            if (fa == fa && fb == fb && opposite_sign(fa, fb)) {
+            double fv[2];
+#pragma unroll 1
+            for (int i = 0; i < 2; ++i) fv[i] = doppler_error(i ? t_guess + hw : t_guess - hw);
+            if (fv[0] == fv[0] && fv[1] == fv[1] && opposite_sign(fv[0], fv[1])) {
                 *aztime = t_guess;
                 err = I3B_SUCCESS;
             }
         }
-        if (err != I3B_SUCCESS) {
-            const double lo = fmax(t_guess - 4.0, t0), hi = fmin(t_guess + 4.0, t1);
-            if (lo < hi) err = brent(lo, hi, doppler_error, prm.tol_aztime, aztime);
+    }
+    if (err != I3B_SUCCESS) {
+        double lo = t0, hi = t1;
+        bool narrow = false;
+        if (t_guess == t_guess) {
+            const double l4 = fmax(t_guess - 4.0, t0), h4 = fmin(t_guess + 4.0, t1);
+            if (l4 < h4) {
+                lo = l4;
+                hi = h4;
+                narrow = true;
+            }
+        }
+#pragma unroll 1
+        for (;;) { // (one call site of the root finder: the Doppler error is inlined once)
+            err = brent(lo, hi, doppler_error, prm.tol_aztime, aztime);
+            if (err == I3B_SUCCESS || !narrow) break;
+            lo = t0;
+            hi = t1;
+            narrow = false;
         }
     }
-    if (err != I3B_SUCCESS) err = brent(t0, t1, doppler_error, prm.tol_aztime, aztime);
     if (err != I3B_SUCCESS) return err;
     orbit_interpolate<LEG>(orbit, *aztime, BORDER_FILLNAN, &xp, &v);
     r = x - xp;

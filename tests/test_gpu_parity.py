@@ -176,6 +176,25 @@ def test_raster_dem_doppler_lut_tsx(oracle):
     check(gpu, cpu, sc)
 
 
+@pytest.mark.parametrize("hmax", [2000.0, 2500.0])
+def test_raster_dem_relief_up_to_the_verge_of_layover(oracle, hmax):
+    """Raster DEMs with 2000 m and 2500 m of relief (largest gradient 0.51 and 0.64 against
+    tan(incidence) = 0.73: steep, nothing lays over yet): the height layer and the image are the
+    reference's.  (These are the two cases that separated a narrow look bracket from the
+    reference's interval when one was tried, see rdr2geo_bracket.)"""
+    import dataclasses
+    sc = synth.make_scene("c4", pulses=2048, bins=2048, out_lines=24, out_samples=180, n_targets=2)
+    d = sc.dem
+    half = 0.5 * abs(d.delta_x) * (d.width - 1)
+    lon_c, lat_c = d.x_start + d.delta_x * (d.width - 1) / 2, d.y_start + d.delta_y * (d.length - 1) / 2
+    dem = synth.synthetic_dem(lon_c, lat_c, half, posting_deg=abs(d.delta_x), hmax=hmax)
+    sc = dataclasses.replace(sc, dem=dem)
+    gpu = run_gpu(sc)
+    cpu = run_cpu(oracle, sc)
+    assert np.nanmax(cpu[2]) - np.nanmin(cpu[2]) > 1.0
+    check(gpu, cpu, sc)
+
+
 def _doppler_lut(geom, method, lo, hi, b_error=False, shape=(7, 9), range_margin=2.0e4, wiggle=25.0):
     """Smooth 2-D Doppler LUT covering ``geom``'s grid (and the whole orbit in time)."""
     g, orbit = geom.radar_grid, geom.orbit
