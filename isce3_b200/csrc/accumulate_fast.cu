@@ -901,8 +901,8 @@ struct NonUniformTag {
 #define I3B_PAIR_RUNS 0
 #endif
 // interior runs that are not steady through the out-of-line per-pulse body: measured slower
-// (0.734 against 0.744 at 9 taps, 0.52 against 0.58 on the airborne frame, where a third of the
-// runs cross a sample boundary) -- the call moves the pair state through memory
+// (0.734 against 0.744 at 9 taps, 0.52 against 0.58 on the airborne frame, where an eighth of the
+// pulses sit in runs that cross a sample boundary) -- the call moves the pair state through memory
 #ifndef I3B_NONSTEADY_CALL
 #define I3B_NONSTEADY_CALL 0
 #endif
