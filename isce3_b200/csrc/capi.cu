@@ -425,14 +425,16 @@ struct Shard {
     const PulseRec* pulse_shared = nullptr;
     const double* pv_shared = nullptr;
     const float2* range_cor_view = nullptr; // per-column output phasors of this shard's columns
-    // One-shot call with page-locked result arrays: parts of the result leave the device while
-    // the accumulation is still running -- the height layer as soon as the target solve is in,
-    // the image rows of every launch but the last as soon as they are final.
+    // One-shot call with host result arrays: parts of the result leave the device while the
+    // accumulation is still running -- the image rows of the last launch's first parts as soon
+    // as they are final, and (page-locked arrays) the height layer as soon as the solve is in.
+    // Copies into pageable arrays block the calling thread, so they are issued only once every
+    // kernel of the call is queued.
     float2* early_out = nullptr;   // this shard's slice of the caller's image (null: no early copies)
     float* early_height = nullptr; // ... of the caller's height layer
+    bool early_pinned = false;     // ... and both are page-locked (copies do not block this thread)
     int out_rows_sent = 0;         // image rows [0, out_rows_sent) are on their way to the host
     bool height_sent = false;
-    std::unique_ptr<Event> ev_part;
 
     ~Shard()
     {
@@ -869,6 +871,11 @@ static void shard_run(const HostScene& hs, Shard& sh, bool resident_only)
                 // The last launch in three parts (3/4, 3/16 and 1/16 of its rows): the image rows
                 // of a part are finalised and copied to the host while the next part is still
                 // being summed, which leaves a sixteenth of the image for after the last kernel.
+                struct PartCopy {
+                    long long first, n;
+                    std::unique_ptr<Event> done;
+                } parts[2];
+                int n_parts = 0;
                 if (sh.early_out) {
                     const int total = sh.nlines - rows_done;
                     for (int part = 0; part < 2; ++part) {
@@ -882,18 +889,30 @@ static void shard_run(const HostScene& hs, Shard& sh, bool resident_only)
                                         sh.range_cor_view, hs.a.mantissa_nbits, s);
                         CK(cudaGetLastError());
                         sh.stats.total_launches += 1;
-                        sh.ev_part.reset(new Event());
-                        sh.ev_part->record(s);
-                        CK(cudaStreamWaitEvent(sh.down, sh.ev_part->e, 0));
-                        CK(cudaMemcpyAsync(sh.early_out + first, sh.out.p + first, (size_t) n * sizeof(float2),
-                                           cudaMemcpyDeviceToHost, sh.down));
-                        sh.stats.d2h_bytes += (int64_t) n * (int64_t) sizeof(float2);
+                        PartCopy& pc = parts[n_parts++];
+                        pc.first = first;
+                        pc.n = n;
+                        pc.done.reset(new Event());
+                        pc.done->record(s);
                         sh.out_rows_sent = r_mid;
                         rows_done = r_mid;
                     }
                 }
                 shard_accumulate(sh, k_split, klast, s, rows_done, sh.nlines, 0);
                 rows_done = sh.nlines;
+                // every kernel is queued: now the copies (into pageable arrays each one returns
+                // when it is done -- by then the GPU is busy with the parts after it)
+                for (int i = 0; i < n_parts; ++i) {
+                    CK(cudaStreamWaitEvent(sh.down, parts[i].done->e, 0));
+                    CK(cudaMemcpyAsync(sh.early_out + parts[i].first, sh.out.p + parts[i].first,
+                                       (size_t) parts[i].n * sizeof(float2), cudaMemcpyDeviceToHost, sh.down));
+                    sh.stats.d2h_bytes += (int64_t) parts[i].n * (int64_t) sizeof(float2);
+                }
+                if (sh.early_height && !sh.height_sent && sh.ap.npix > 0 && n_parts > 0) {
+                    CK(cudaMemcpyAsync(sh.early_height, sh.height.p, sh.height.n * sizeof(float), cudaMemcpyDeviceToHost, sh.down));
+                    sh.stats.d2h_bytes += (int64_t) (sh.height.n * sizeof(float));
+                    sh.height_sent = true;
+                }
                 return;
             }
             const int have = n_landed ? slab_end[n_landed - 1] : b0;
@@ -922,7 +941,7 @@ static void shard_run(const HostScene& hs, Shard& sh, bool resident_only)
                 shard_solve_finish(sh); // (blocks only when every slab is already queued)
                 solved = true;
                 t_solved = since();
-                if (sh.early_height && sh.ap.npix > 0) {
+                if (sh.early_height && sh.early_pinned && sh.ap.npix > 0) {
                     // the height layer is the solve's own output: final already
                     CK(cudaMemcpyAsync(sh.early_height, sh.height.p, sh.height.n * sizeof(float), cudaMemcpyDeviceToHost, sh.down));
                     sh.stats.d2h_bytes += (int64_t) (sh.height.n * sizeof(float));
@@ -1641,11 +1660,11 @@ int i3b_backproject(const I3B_BackprojectArgs* args)
             // starts doing so while the target solve is still running
             shard_solve_launch(plan->hs, sh);
             if (single) t_solve = lap();
-            if (!(args->flags & I3B_FLAG_DEVICE_POINTERS) && host_is_page_locked(out) &&
-                (!height || host_is_page_locked(height))) {
+            if (!(args->flags & I3B_FLAG_DEVICE_POINTERS)) {
                 const size_t off = (size_t) sh.line0 * (size_t) args->out_geometry.grid.width;
                 sh.early_out = reinterpret_cast<float2*>(out) + off;
                 sh.early_height = height ? height + off : nullptr;
+                sh.early_pinned = host_is_page_locked(out) && (!height || host_is_page_locked(height));
             }
             shard_run(plan->hs, sh, false);
             if (single) t_run = lap();
