@@ -188,6 +188,10 @@ typedef struct {
     uint32_t abi_version; /* = I3B_ABI_VERSION */
     uint32_t flags;       /* I3B_FLAG_* */
 
+    /* Host arrays (pageable or page-locked; page-locked ones make every copy asynchronous:
+     * the upload then hides behind the target solve and the accumulation, the results leave
+     * the device while the last rows are still being summed), or device arrays with
+     * I3B_FLAG_DEVICE_POINTERS / I3B_FLAG_DEVICE_INPUT.                                   */
     float* out;      /* complex64 [out.length][out.width] interleaved re,im  */
     const float* in; /* complex64 [in.length][in.width] range-compressed     */
     float* height;   /* float32 [out.length][out.width] or NULL              */
